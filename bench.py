@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the ctdet heat-map decode hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one ctdet_decode pass (3x3 peak-NMS + top-K + wh/reg gather + box assembly)
+over one synthetic batch: BASELINE configs[1] geometry, 64 images per GPU of
+80x128x128 post-sigmoid heat + wh + reg, K=100.  Weak scaling: every rank decodes its
+own 64-image shard, no data-path collective.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max
+over ranks); `e2e` = same metric through the public API with pinned HOST buffers, the
+H2D of the heat/wh/reg batch and the D2H of the detections inside the timed region;
+`roofline` = algorithmic bytes / device time against MEASURED_PEAKS.json;
+`cpu_baseline` = the CPU port of the reference path on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec ctdet 512x512->128x128x80 heatmap decode K=100"
+UNIT = "images/s"
+B_PER_GPU, C, H, W, K = 64, 80, 128, 128, 100
+ALG_BYTES_PER_IMAGE = C * H * W * 4 + K * 4 * 4 + K * 6 * 4   # 5,246,880 B
+N_ROT = 3                                                      # rotating input batches (3 x 352 MB >> 126 MB L2)
+
+
+def synth(batch, device, seed):
+    """SURVEY.md section 8d synthetic inputs: heat = sigmoid(randn - 2.19), wh = rand*32, reg = rand."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    heat = torch.sigmoid(torch.randn(batch, C, H, W, device=device, generator=g) - 2.19)
+    wh = torch.rand(batch, 2, H, W, device=device, generator=g) * 32
+    reg = torch.rand(batch, 2, H, W, device=device, generator=g)
+    return heat, wh, reg
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # no NVML: report that instead of inventing numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_rate(batch, repeats, threads):
+    """images/s of the CPU port of the reference path (oracle/torch_port.py) on `batch` images."""
+    from oracle import torch_port
+    torch.set_num_threads(threads)
+    heat, wh, reg = synth(batch, "cpu", 317)
+    torch_port.ctdet_decode(heat, wh, reg, K=K)  # warm-up
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        torch_port.ctdet_decode(heat, wh, reg, K=K)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return batch / ts[len(ts) // 2], ts
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU port of the reference's PyTorch path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_b = 16
+    torch.set_num_threads(cores)
+    from oracle import torch_port
+    heat, wh, reg = synth(sample_b, "cpu", 317)
+    for _ in range(max(1, min(args.warmup, 2))):
+        torch_port.ctdet_decode(heat, wh, reg, K=K)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        torch_port.ctdet_decode(heat, wh, reg, K=K)
+    dt = time.perf_counter() - t0
+    value = sample_b * args.steps / dt
+    sample = "each step = %d of the %d images of a batch (same synthetic distribution), torch CPU ops" % (
+        sample_b, B_PER_GPU)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ctdet decode, %d img x %dx%dx%d heat + wh + reg, K=%d (BASELINE configs[1] geometry)"
+                   % (B_PER_GPU, C, H, W, K), "global_batch": B_PER_GPU * args.gpus},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the decode path has no CPU fallback")
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import centernet_b200
+    from centernet_b200 import decode as D
+    from centernet_b200._lib import C as CL
+
+    batches = [synth(B_PER_GPU, dev, 317 + 1000 * rank + i) for i in range(N_ROT)]
+    for i in range(max(args.warmup, 3)):
+        D.ctdet_decode(*batches[i % N_ROT][:2], reg=batches[i % N_ROT][2], K=K)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (CUDA events on the launching stream)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = CL.launch_count()
+    ev0.record()
+    for i in range(args.steps):
+        h, w_, r = batches[i % N_ROT]
+        dets = D.ctdet_decode(h, w_, reg=r, K=K)
+    ev1.record()
+    barrier()
+    launches = CL.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = B_PER_GPU * world * args.steps / (ms_max * 1e-3)
+
+    # ---------------- end-to-end: pinned host buffers -> H2D -> decode -> D2H of the detections
+    host = [tuple(x.cpu().pin_memory() for x in batches[i]) for i in range(2)]
+    h2d = sum(x.numel() * 4 for x in host[0])
+    d2h = B_PER_GPU * K * 6 * 4
+    for i in range(2):
+        D.ctdet_decode_from_host(*host[i % 2][:2], reg=host[i % 2][2], K=K)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.e2e_steps):
+        out = D.ctdet_decode_from_host(*host[i % 2][:2], reg=host[i % 2][2], K=K)   # returns a host tensor
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B_PER_GPU * world * args.e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        # the decode call is stage-1 (streams the heat map) + a small finalize kernel; the
+        # roofline is reported on the whole call, i.e. conservatively for the dominant kernel
+        per_launch_s = ms_max * 1e-3 / args.steps
+        achieved = ALG_BYTES_PER_IMAGE * B_PER_GPU / per_launch_s / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "ctdet decode, %d img/GPU x %dx%dx%d post-sigmoid heat + wh + reg, K=%d "
+                            "(BASELINE configs[1] geometry: DLA-34 512x512 batch=64 heads)" % (B_PER_GPU, C, H, W, K),
+                "global_batch": B_PER_GPU * world, "parallelism": "dp%d (batch shards, no collective)" % world,
+                "l2": "inputs > L2: %d rotating batches of %.0f MB" % (N_ROT, h2d / 1e6),
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_select_stage1 + k_select_finalize (whole decode call)",
+                         "alg_bytes_per_launch": ALG_BYTES_PER_IMAGE * B_PER_GPU},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": args.e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "lib_version": centernet_b200.version(),
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, ts = cpu_port_rate(16, 5, cores)
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "16 images of the same synthetic distribution, median of 5 runs, "
+                                             "torch CPU op port of the reference path (oracle/torch_port.py)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

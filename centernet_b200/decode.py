@@ -1,0 +1,260 @@
+"""Mirror of src/lib/models/decode.py: same names, signatures, defaults and outputs.
+
+Every function takes fp32 CUDA tensors (NCHW; heat maps already sigmoided by the
+caller, as in detectors/ctdet.py:31,40), does not mutate its inputs, and returns a new
+fp32 tensor on the same device, enqueued on the current stream.  The work is done by
+the hand-written sm_100a kernels behind ``include/centernet_b200.h``; there is no
+CPU path (non-CUDA inputs raise NotImplementedError).
+
+Tie order, which the reference leaves to torch.topk, is defined here as
+(score desc, flat index cls*H*W + y*W + x asc).
+"""
+import torch
+
+from ._lib import C, f32c, ptr, require_cuda, stream_ptr, workspace
+from .utils import _gather_feat, _transpose_and_gather_feat  # noqa: F401  (re-exported like the reference)
+
+
+def _dims(t):
+    b, c, h, w = t.shape
+    return int(b), int(c), int(h), int(w)
+
+
+# ------------------------------------------------------------------ decode.py:9-15
+def _nms(heat, kernel=3):
+    if kernel != 3:
+        raise NotImplementedError("_nms: only the 3x3 kernel the reference uses is implemented")
+    require_cuda(heat, what="_nms")
+    heat = f32c(heat)
+    b, c, h, w = _dims(heat)
+    out = torch.empty_like(heat)
+    if heat.numel():
+        C.nms(ptr(heat), ptr(out), b, c, h, w, stream_ptr(heat))
+    return out
+
+
+# ------------------------------------------------------------------ decode.py:17-77
+def _aggregate(heat, aggr_weight, horizontal):
+    require_cuda(heat, what="_aggregate")
+    heat = f32c(heat)
+    b, c, h, w = _dims(heat)
+    out = torch.empty_like(heat)
+    C.edge_aggregate(ptr(heat), ptr(out), b, c, h, w, float(aggr_weight), int(horizontal), stream_ptr(heat))
+    return out
+
+
+def _h_aggregate(heat, aggr_weight=0.1):
+    """decode.py:71-73: aggr_weight*left + aggr_weight*right + heat (one fused scan kernel)."""
+    return _aggregate(heat, aggr_weight, True)
+
+
+def _v_aggregate(heat, aggr_weight=0.1):
+    """decode.py:75-77."""
+    return _aggregate(heat, aggr_weight, False)
+
+
+def _left_aggregate(heat):
+    """decode.py:17-28.  Derived from the fused kernel's directional outputs."""
+    return _directional(heat, 0)
+
+
+def _right_aggregate(heat):
+    """decode.py:30-41."""
+    return _directional(heat, 1)
+
+
+def _top_aggregate(heat):
+    """decode.py:43-55."""
+    return _directional(heat, 2)
+
+
+def _bottom_aggregate(heat):
+    """decode.py:57-69."""
+    return _directional(heat, 3)
+
+
+def _directional(heat, direction):
+    # weight=1 with the opposite direction disabled is encoded as horizontal = 2 + direction
+    require_cuda(heat, what="_aggregate")
+    heat = f32c(heat)
+    b, c, h, w = _dims(heat)
+    out = torch.empty_like(heat)
+    C.edge_aggregate(ptr(heat), ptr(out), b, c, h, w, 1.0, 2 + direction, stream_ptr(heat))
+    return out
+
+
+# ------------------------------------------------------------------ decode.py:92-119
+def _topk_channel(scores, K=40):
+    require_cuda(scores, what="_topk_channel")
+    scores = f32c(scores)
+    b, c, h, w = _dims(scores)
+    dev = scores.device
+    s = torch.empty((b, c, K), dtype=torch.float32, device=dev)
+    inds = torch.empty((b, c, K), dtype=torch.int64, device=dev)
+    ys = torch.empty((b, c, K), dtype=torch.float32, device=dev)
+    xs = torch.empty((b, c, K), dtype=torch.float32, device=dev)
+    nb = C.topk_workspace_bytes(b * c, 1, h, w, K)
+    ws = workspace(nb, dev)
+    C.topk_channel(ptr(scores), b, c, h, w, K, 0, ptr(s), ptr(inds), ptr(ys), ptr(xs), ptr(ws), ws.numel(),
+                   stream_ptr(scores))
+    return s, inds, ys, xs
+
+
+def _topk(scores, K=40):
+    require_cuda(scores, what="_topk")
+    scores = f32c(scores)
+    b, c, h, w = _dims(scores)
+    dev = scores.device
+    s = torch.empty((b, K), dtype=torch.float32, device=dev)
+    inds = torch.empty((b, K), dtype=torch.int64, device=dev)
+    clses = torch.empty((b, K), dtype=torch.int32, device=dev)
+    ys = torch.empty((b, K), dtype=torch.float32, device=dev)
+    xs = torch.empty((b, K), dtype=torch.float32, device=dev)
+    nb = C.topk_workspace_bytes(b, c, h, w, K)
+    ws = workspace(nb, dev)
+    C.topk(ptr(scores), b, c, h, w, K, 0, ptr(s), ptr(inds), ptr(clses), ptr(ys), ptr(xs), ptr(ws), ws.numel(),
+           stream_ptr(scores))
+    return s, inds, clses, ys, xs
+
+
+# ------------------------------------------------------------------ decode.py:464-495
+def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100):
+    require_cuda(heat, wh, reg, what="ctdet_decode")
+    heat, wh, reg = f32c(heat), f32c(wh), f32c(reg)
+    b, c, h, w = _dims(heat)
+    want = 2 * c if cat_spec_wh else 2
+    if wh.shape[0] != b or wh.shape[1] != want or tuple(wh.shape[2:]) != (h, w):
+        raise RuntimeError("ctdet_decode: wh must be [%d, %d, %d, %d], got %s" % (b, want, h, w, tuple(wh.shape)))
+    if reg is not None and tuple(reg.shape) != (b, 2, h, w):
+        raise RuntimeError("ctdet_decode: reg must be [%d, 2, %d, %d], got %s" % (b, h, w, tuple(reg.shape)))
+    dets = torch.empty((b, K, 6), dtype=torch.float32, device=heat.device)
+    ws = workspace(C.topk_workspace_bytes(b, c, h, w, K), heat.device)
+    C.ctdet_decode(ptr(heat), ptr(wh), ptr(reg), int(bool(cat_spec_wh)), b, c, h, w, K, ptr(dets), ptr(ws),
+                   ws.numel(), stream_ptr(heat))
+    return dets
+
+
+# ------------------------------------------------------------------ decode.py:426-462
+def ddd_decode(heat, rot, depth, dim, wh=None, reg=None, K=40):
+    require_cuda(heat, rot, depth, dim, wh, reg, what="ddd_decode")
+    heat, rot, depth, dim, wh, reg = [f32c(t) for t in (heat, rot, depth, dim, wh, reg)]
+    b, c, h, w = _dims(heat)
+    for name, t, ch in (("rot", rot, 8), ("depth", depth, 1), ("dim", dim, 3), ("wh", wh, 2), ("reg", reg, 2)):
+        if t is not None and tuple(t.shape) != (b, ch, h, w):
+            raise RuntimeError("ddd_decode: %s must be [%d, %d, %d, %d], got %s" % (name, b, ch, h, w, tuple(t.shape)))
+    dets = torch.empty((b, K, 18 if wh is not None else 16), dtype=torch.float32, device=heat.device)
+    ws = workspace(C.topk_workspace_bytes(b, c, h, w, K), heat.device)
+    C.ddd_decode(ptr(heat), ptr(rot), ptr(depth), ptr(dim), ptr(wh), ptr(reg), b, c, h, w, K, ptr(dets), ptr(ws),
+                 ws.numel(), stream_ptr(heat))
+    return dets
+
+
+# ------------------------------------------------------------------ decode.py:497-571
+def multi_pose_decode(heat, wh, kps, reg=None, hm_hp=None, hp_offset=None, K=100):
+    require_cuda(heat, wh, kps, reg, hm_hp, hp_offset, what="multi_pose_decode")
+    heat, wh, kps, reg, hm_hp, hp_offset = [f32c(t) for t in (heat, wh, kps, reg, hm_hp, hp_offset)]
+    b, c, h, w = _dims(heat)
+    j = int(kps.shape[1]) // 2
+    for name, t, ch in (("wh", wh, 2), ("kps", kps, 2 * j), ("reg", reg, 2), ("hm_hp", hm_hp, j),
+                        ("hp_offset", hp_offset, 2)):
+        if t is not None and tuple(t.shape) != (b, ch, h, w):
+            raise RuntimeError("multi_pose_decode: %s must be [%d, %d, %d, %d], got %s"
+                               % (name, b, ch, h, w, tuple(t.shape)))
+    dets = torch.empty((b, K, 4 + 1 + 2 * j + 1), dtype=torch.float32, device=heat.device)
+    ws = workspace(C.multi_pose_workspace_bytes(b, c, j, h, w, K), heat.device)
+    C.multi_pose_decode(ptr(heat), ptr(wh), ptr(kps), ptr(reg), ptr(hm_hp), ptr(hp_offset), b, c, j, h, w, K,
+                        ptr(dets), ptr(ws), ws.numel(), stream_ptr(heat))
+    return dets
+
+
+# ------------------------------------------------------------------ decode.py:122-424
+def _exct(t_heat, l_heat, b_heat, r_heat, ct_heat, regs, K, scores_thresh, center_thresh, aggr_weight, num_dets,
+          agnostic, name):
+    require_cuda(t_heat, l_heat, b_heat, r_heat, ct_heat, *regs, what=name)
+    t_heat, l_heat, b_heat, r_heat, ct_heat = [f32c(t) for t in (t_heat, l_heat, b_heat, r_heat, ct_heat)]
+    b, c, h, w = _dims(t_heat)
+    cc = int(ct_heat.shape[1])
+    for t in (l_heat, b_heat, r_heat):
+        if tuple(t.shape) != (b, c, h, w):
+            raise RuntimeError("%s: extreme-point heat maps must share one shape" % name)
+    if all(r is not None for r in regs):  # decode.py:366-367: all four or none
+        regs = [f32c(r) for r in regs]
+    else:
+        regs = [None] * 4
+    dets = torch.empty((b, num_dets, 14), dtype=torch.float32, device=t_heat.device)
+    ws = workspace(C.exct_workspace_bytes(b, c, cc, h, w, K, num_dets), t_heat.device)
+    C.exct_decode(ptr(t_heat), ptr(l_heat), ptr(b_heat), ptr(r_heat), ptr(ct_heat), ptr(regs[0]), ptr(regs[1]),
+                  ptr(regs[2]), ptr(regs[3]), b, c, cc, h, w, K, float(scores_thresh), float(center_thresh),
+                  float(aggr_weight), int(num_dets), int(agnostic), ptr(dets), ptr(ws), ws.numel(),
+                  stream_ptr(t_heat))
+    return dets
+
+
+def agnex_ct_decode(t_heat, l_heat, b_heat, r_heat, ct_heat, t_regr=None, l_regr=None, b_regr=None, r_regr=None,
+                    K=40, scores_thresh=0.1, center_thresh=0.1, aggr_weight=0.0, num_dets=1000):
+    return _exct(t_heat, l_heat, b_heat, r_heat, ct_heat, (t_regr, l_regr, b_regr, r_regr), K, scores_thresh,
+                 center_thresh, aggr_weight, num_dets, True, "agnex_ct_decode")
+
+
+def exct_decode(t_heat, l_heat, b_heat, r_heat, ct_heat, t_regr=None, l_regr=None, b_regr=None, r_regr=None,
+                K=40, scores_thresh=0.1, center_thresh=0.1, aggr_weight=0.0, num_dets=1000):
+    return _exct(t_heat, l_heat, b_heat, r_heat, ct_heat, (t_regr, l_regr, b_regr, r_regr), K, scores_thresh,
+                 center_thresh, aggr_weight, num_dets, False, "exct_decode")
+
+
+# ------------------------------------------------------------------ host-buffer entry (end-to-end path)
+_HOST_CTX = {}
+
+
+def ctdet_decode_from_host(heat, wh, reg=None, cat_spec_wh=False, K=100, chunk=8, device=None):
+    """ctdet_decode for HOST tensors (pinned memory recommended): the batch is cut into
+    `chunk`-image pieces whose H2D copies run on a side stream, double-buffered against the
+    decode kernels of the previous piece; the [B, K, 6] detections come back in pinned host
+    memory.  This is the call a detector makes when the heat maps are produced off-device
+    (and what bench.py times as `e2e`).  Same semantics as ctdet_decode."""
+    if heat.is_cuda:
+        return ctdet_decode(heat, wh, reg=reg, cat_spec_wh=cat_spec_wh, K=K).cpu()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    heat, wh, reg = f32c(heat), f32c(wh), f32c(reg)
+    b, c, h, w = _dims(heat)
+    chunk = max(1, min(chunk, b))
+    key = (dev.index, c, h, w, int(wh.shape[1]), reg is not None, chunk, b, K)
+    ctx = _HOST_CTX.get(key)
+    if ctx is None:
+        ctx = {
+            "copy": torch.cuda.Stream(device=dev),
+            "heat": [torch.empty((chunk, c, h, w), dtype=torch.float32, device=dev) for _ in range(2)],
+            "wh": [torch.empty((chunk, int(wh.shape[1]), h, w), dtype=torch.float32, device=dev) for _ in range(2)],
+            "reg": [torch.empty((chunk, 2, h, w), dtype=torch.float32, device=dev) for _ in range(2)]
+                   if reg is not None else [None, None],
+            "dets": torch.empty((b, K, 6), dtype=torch.float32, device=dev),
+            "out": torch.empty((b, K, 6), dtype=torch.float32).pin_memory(),
+            "ws": workspace(C.topk_workspace_bytes(chunk, c, h, w, K), dev),
+            "free": [torch.cuda.Event(), torch.cuda.Event()],
+            "ready": [torch.cuda.Event(), torch.cuda.Event()],
+        }
+        _HOST_CTX.clear()  # keep one geometry resident
+        _HOST_CTX[key] = ctx
+    main = torch.cuda.current_stream(dev)
+    copy = ctx["copy"]
+    copy.wait_stream(main)
+    for i, s in enumerate(range(0, b, chunk)):
+        n = min(chunk, b - s)
+        slot = i & 1
+        with torch.cuda.stream(copy):
+            if i >= 2:
+                copy.wait_event(ctx["free"][slot])
+            ctx["heat"][slot][:n].copy_(heat[s:s + n], non_blocking=True)
+            ctx["wh"][slot][:n].copy_(wh[s:s + n], non_blocking=True)
+            if reg is not None:
+                ctx["reg"][slot][:n].copy_(reg[s:s + n], non_blocking=True)
+            ctx["ready"][slot].record(copy)
+        main.wait_event(ctx["ready"][slot])
+        dets = ctx["dets"][s:s + n]
+        C.ctdet_decode(ptr(ctx["heat"][slot]), ptr(ctx["wh"][slot]), ptr(ctx["reg"][slot]),
+                       int(bool(cat_spec_wh)), n, c, h, w, K, ptr(dets), ptr(ctx["ws"]), ctx["ws"].numel(),
+                       main.cuda_stream)
+        ctx["free"][slot].record(main)
+    ctx["out"].copy_(ctx["dets"], non_blocking=True)
+    main.synchronize()
+    return ctx["out"]

@@ -1,0 +1,194 @@
+/*
+ * centernet_b200 -- C ABI of the B200-native CenterNet heat-map hot path.
+ *
+ * This is the drop-in boundary: plain device pointers, explicit sizes and a
+ * CUDA stream handle; no torch types.  The reference has two bindings on this
+ * path and both are replaced here:
+ *
+ *   (1) the Python ATen-op functions of src/lib/models/decode.py,
+ *       src/lib/models/utils.py and src/lib/models/losses.py (no FFI of their
+ *       own -- each cnb_* entry below names the function it replaces), and
+ *   (2) the cffi module `_ext.dcn_v2` declared in
+ *       src/lib/models/networks/DCNv2/src/dcn_v2_cuda.h:9-55
+ *       (dcn_v2_cuda_forward / dcn_v2_cuda_backward / dcn_v2_psroi_pooling_*).
+ *
+ * Conventions
+ *   - every tensor is fp32, NCHW, contiguous, resident on the current device;
+ *     index outputs use the reference's dtypes (int64 indices, int32 classes);
+ *   - the caller owns every buffer, including the scratch `workspace`
+ *     (size from the matching cnb_*_workspace_bytes); the library never calls
+ *     cudaMalloc and keeps no global mutable state, so it may be called from
+ *     one thread per GPU concurrently (torch DataParallel style);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *     nothing synchronises the host;
+ *   - return value: CNB_OK or an error code; cnb_last_error() gives a
+ *     thread-local description.  The reference's THArgCheck/THError
+ *     (dcn_v2_cuda.c:20-38) map to CNB_EINVAL.
+ */
+#ifndef CENTERNET_B200_H_
+#define CENTERNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNB_OK 0
+#define CNB_EINVAL 1       /* bad shape / null pointer / misaligned buffer        */
+#define CNB_EUNSUPPORTED 2 /* valid request outside the implemented envelope     */
+#define CNB_ECUDA 3        /* CUDA runtime / launch error                        */
+#define CNB_EWORKSPACE 4   /* workspace_bytes smaller than cnb_*_workspace_bytes */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int cnb_version(void);
+/* Thread-local text of the last error returned on this thread ("" if none). */
+const char *cnb_last_error(void);
+/* Number of kernels launched by this library since process start (all threads);
+ * bench.py reports it as `gpu_launches`. */
+unsigned long long cnb_launch_count(void);
+
+/* ---------------------------------------------------------------- A1: _nms
+ * models/decode.py:9-15.  out = heat * (maxpool3x3(heat) == heat).
+ * heat,out: [n, c, h, w]. */
+int cnb_nms(const float *heat, float *out, int n, int c, int h, int w, void *stream);
+
+/* ------------------------------------------------------------- A2/A3: top-K
+ * Workspace for every selection-based entry point below (depends on the
+ * largest (n_img, c, h, w, k) the call processes). */
+size_t cnb_topk_workspace_bytes(int n_img, int c, int h, int w, int k);
+
+/* models/decode.py:103-119 (_topk).  scores: [b, c, h, w] (already NMS'd by the
+ * caller, as in the reference) -> per image the K best over all classes:
+ * out_scores[b,k] f32, out_inds[b,k] i64 (y*w+x), out_clses[b,k] i32,
+ * out_ys/out_xs[b,k] f32.  Order: score desc, ties by flat index asc.
+ * fuse_nms != 0 applies the 3x3 peak test of _nms first (scores = raw heat). */
+int cnb_topk(const float *scores, int b, int c, int h, int w, int k, int fuse_nms,
+             float *out_scores, int64_t *out_inds, int32_t *out_clses,
+             float *out_ys, float *out_xs,
+             void *workspace, size_t workspace_bytes, void *stream);
+
+/* models/decode.py:92-101 (_topk_channel): per (b, channel) top-K.
+ * Outputs are [b, c, k]. */
+int cnb_topk_channel(const float *scores, int b, int c, int h, int w, int k, int fuse_nms,
+                     float *out_scores, int64_t *out_inds, float *out_ys, float *out_xs,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* --------------------------------------------------------------- A4: gather
+ * models/utils.py:22-26 (_transpose_and_gather_feat) without the transpose
+ * copy: out[b, m, ch] = feat[b, ch, ind[b, m]];  feat [b, c, h*w], ind [b, m]. */
+int cnb_gather_feat(const float *feat, const int64_t *ind, float *out,
+                    int b, int c, int hw, int m, void *stream);
+
+/* ---------------------------------------------------------- A5: ctdet_decode
+ * models/decode.py:464-495.  heat [b,c,h,w] (post-sigmoid), wh [b,2,h,w] (or
+ * [b,2c,h,w] when cat_spec_wh), reg [b,2,h,w] or NULL -> dets [b,k,6] =
+ * x1,y1,x2,y2,score,class.  One fused pass: peak-NMS + top-K + gathers. */
+int cnb_ctdet_decode(const float *heat, const float *wh, const float *reg, int cat_spec_wh,
+                     int b, int c, int h, int w, int k, float *dets,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------ A9: ddd_decode
+ * models/decode.py:426-462.  rot [b,8,h,w], depth [b,1,h,w], dim [b,3,h,w],
+ * wh/reg [b,2,h,w] or NULL -> dets [b,k,18] (16 when wh == NULL). */
+int cnb_ddd_decode(const float *heat, const float *rot, const float *depth, const float *dim,
+                   const float *wh, const float *reg, int b, int c, int h, int w, int k,
+                   float *dets, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ----------------------------------------------------- A6: multi_pose_decode
+ * models/decode.py:497-571.  heat [b,1,h,w]; wh, reg(NULL ok) [b,2,h,w];
+ * kps [b,2j,h,w]; hm_hp [b,j,h,w] or NULL; hp_offset [b,2,h,w] or NULL
+ * -> dets [b,k,4+1+2j+1]. */
+size_t cnb_multi_pose_workspace_bytes(int b, int c, int j, int h, int w, int k);
+int cnb_multi_pose_decode(const float *heat, const float *wh, const float *kps, const float *reg,
+                          const float *hm_hp, const float *hp_offset,
+                          int b, int c, int j, int h, int w, int k, float *dets,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------ A7: edge aggregation
+ * models/decode.py:17-77.  out = heat + weight*(dirA + dirB) with
+ * horizontal != 0: _h_aggregate (left+right), else _v_aggregate (top+bottom).
+ * Strictly sequential fp32 running sums, as the reference. */
+int cnb_edge_aggregate(const float *heat, float *out, int n, int c, int h, int w,
+                       float aggr_weight, int horizontal, void *stream);
+
+/* ------------------------------------------- A8: exct_decode / agnex_ct_decode
+ * models/decode.py:273-424 and :122-271.  t,l,b,r heat [b,c,h,w] (c==1 for
+ * agnostic), ct heat [b,cc,h,w]; regr [b,2,h,w] each or all NULL
+ * -> dets [b,num_dets,14]. */
+size_t cnb_exct_workspace_bytes(int b, int c, int cc, int h, int w, int k, int num_dets);
+int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_heat,
+                    const float *r_heat, const float *ct_heat,
+                    const float *t_regr, const float *l_regr, const float *b_regr,
+                    const float *r_regr, int b, int c, int cc, int h, int w, int k,
+                    float scores_thresh, float center_thresh, float aggr_weight,
+                    int num_dets, int agnostic, float *dets,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------- A13/A14/A15: focal + splat
+ * _sigmoid (models/utils.py:8-10), _neg_loss (models/losses.py:42-67) and the
+ * Gaussian target splat draw_umich_gaussian (utils/image.py:126-141) fused.
+ *
+ * cnb_focal_loss: pred/gt [n] flat (gt given as a dense map, reference form).
+ *   logits != 0: `pred` holds raw logits and _sigmoid (clamped) is applied
+ *   first.  Writes out[0]=loss, out[1]=num_pos; grad (nullable) receives
+ *   d loss / d pred (or / d logit when logits != 0) scaled by grad_scale.
+ * cnb_focal_splat_loss: same loss but the target map is never materialised:
+ *   it is rebuilt on the fly from per-image object lists
+ *   obj_cls[b,m] i32, obj_cx/obj_cy[b,m] i32 (ct_int), obj_radius[b,m] i32,
+ *   obj_valid[b,m] u8 -- exactly the draw_umich_gaussian calls of
+ *   datasets/sample/ctdet.py:111-117. */
+size_t cnb_focal_workspace_bytes(long long n);
+int cnb_focal_loss(const float *pred, const float *gt, long long n, int logits,
+                   float grad_scale, float *out2, float *grad,
+                   void *workspace, size_t workspace_bytes, void *stream);
+int cnb_splat_gaussian(const int32_t *obj_cls, const int32_t *obj_cx, const int32_t *obj_cy,
+                       const int32_t *obj_radius, const uint8_t *obj_valid, int b, int m,
+                       int c, int h, int w, float *hm, void *stream);
+int cnb_focal_splat_loss(const float *pred, const int32_t *obj_cls, const int32_t *obj_cx,
+                         const int32_t *obj_cy, const int32_t *obj_radius,
+                         const uint8_t *obj_valid, int b, int m, int c, int h, int w,
+                         int logits, float grad_scale, float *out2, float *grad,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------ A16: RegL1Loss
+ * models/losses.py:139-149 (mode 0), RegLoss smooth-L1 :123-137 (mode 1),
+ * NormRegL1Loss :151-163 (mode 2), RegWeightedL1Loss :165-175 (mode 3; mask is
+ * then float [b,m,d]).  output [b,d,h*w], ind [b,m] i64, target [b,m,d].
+ * out[0] = loss; grad_output (nullable, [b,d,hw], must be zero-filled) gets
+ * d loss/d output * grad_scale. */
+int cnb_reg_loss(const float *output, const void *mask, const int64_t *ind, const float *target,
+                 int b, int d, int hw, int m, int mode, float grad_scale,
+                 float *out1, float *grad_output, void *stream);
+
+/* ---------------------------------------------------------- A10/A11: DCNv2
+ * Replaces dcn_v2_cuda_forward / dcn_v2_cuda_backward
+ * (DCNv2/src/dcn_v2_cuda.h:9-33, dcn_v2_cuda.c:10-241).  im2col-free: no
+ * `columns` / `ones` scratch.  input [b,cin,h,w], offset [b,2*kh*kw*dg,ho,wo]
+ * (channel 2t = dy, 2t+1 = dx of tap t), mask [b,kh*kw*dg,ho,wo],
+ * weight [cout,cin,kh,kw], bias [cout] -> output [b,cout,ho,wo].
+ * Backward ACCUMULATES into grad_weight/grad_bias and overwrites
+ * grad_input/grad_offset/grad_mask, which must arrive zero-filled as in
+ * dcn_v2_func.py:44-48. */
+size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
+                                 int stride, int pad, int dil, int dg);
+int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask,
+                      const float *weight, const float *bias, float *output,
+                      int b, int cin, int h, int w, int cout, int kh, int kw,
+                      int stride_h, int stride_w, int pad_h, int pad_w,
+                      int dil_h, int dil_w, int deformable_groups,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int cnb_dcnv2_backward(const float *input, const float *offset, const float *mask,
+                       const float *weight, const float *grad_output,
+                       float *grad_input, float *grad_offset, float *grad_mask,
+                       float *grad_weight, float *grad_bias,
+                       int b, int cin, int h, int w, int cout, int kh, int kw,
+                       int stride_h, int stride_w, int pad_h, int pad_w,
+                       int dil_h, int dil_w, int deformable_groups,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CENTERNET_B200_H_ */

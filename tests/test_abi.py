@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads and exports every symbol include/centernet_b200.h declares;
+argument validation works without a GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "centernet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cnb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = ctypes.CDLL(os.path.join(ROOT, "centernet_b200", "lib", "libcenternet_b200.so"))
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    lib.cnb_version.restype = ctypes.c_int
+    assert lib.cnb_version() >= 100
+
+
+def test_pybind_layer_and_validation():
+    from centernet_b200 import _C
+    assert _C.version() >= 100
+    assert _C.topk_workspace_bytes(64, 80, 128, 128, 100) > 0
+    # bad arguments are rejected before any CUDA call (status EINVAL -> RuntimeError)
+    with pytest.raises(RuntimeError, match="null pointer"):
+        _C.ctdet_decode(0, 0, 0, 0, 1, 80, 128, 128, 100, 0, 0, 0, 0)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        _C.topk(16, 1, 1, 4, 4, 17, 0, 0, 0, 0, 0, 0, 16, 1 << 20, 0)
+    assert "exceeds" in _C.last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+    from centernet_b200 import decode
+    with pytest.raises(NotImplementedError):
+        decode.ctdet_decode(torch.rand(1, 2, 8, 8), torch.rand(1, 2, 8, 8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "centernet_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "oracle/" not in txt and "oracle." not in txt, f
