@@ -49,6 +49,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.recording = False      # only samples taken inside the timed region are kept
+        self.alive = threading.Event()
 
     def run(self):
         try:
@@ -63,17 +65,21 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             }
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+                self.alive.set()
+                if self.recording:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.002)
         except Exception as e:  # no NVML: report that instead of inventing numbers
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+            self.alive.set()
 
     def summary(self):
         s = sorted(self.samples)
@@ -139,7 +145,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=20)
@@ -179,15 +185,18 @@ def main():
     # ---------------- device-resident timing (CUDA events on the launching stream)
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.alive.wait(timeout=10)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = CL.launch_count()
+    sampler.recording = True
     ev0.record()
     for i in range(args.steps):
         h, w_, r = batches[i % N_ROT]
         dets = D.ctdet_decode(h, w_, reg=r, K=K)
     ev1.record()
     barrier()
+    sampler.recording = False
     launches = CL.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
     sampler.stop_flag = True
@@ -199,24 +208,26 @@ def main():
     value = B_PER_GPU * world * args.steps / (ms_max * 1e-3)
 
     # ---------------- end-to-end: pinned host buffers -> H2D -> decode -> D2H of the detections
-    host = [tuple(x.cpu().pin_memory() for x in batches[i]) for i in range(2)]
-    h2d = sum(x.numel() * 4 for x in host[0])
+    h2d = sum(x.numel() * 4 for x in batches[0])
     d2h = B_PER_GPU * K * 6 * 4
-    for i in range(2):
-        D.ctdet_decode_from_host(*host[i % 2][:2], reg=host[i % 2][2], K=K)
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.e2e_steps):
-        out = D.ctdet_decode_from_host(*host[i % 2][:2], reg=host[i % 2][2], K=K)   # returns a host tensor
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B_PER_GPU * world * args.e2e_steps / (float(t.item()) * 1e-3)
+    e2e_value = None
+    if args.e2e_steps > 0:
+        host = [tuple(x.cpu().pin_memory() for x in batches[i]) for i in range(2)]
+        for i in range(2):
+            D.ctdet_decode_from_host(*host[i % 2][:2], reg=host[i % 2][2], K=K)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.e2e_steps):
+            out = D.ctdet_decode_from_host(*host[i % 2][:2], reg=host[i % 2][2], K=K)   # returns a host tensor
+        e1.record()
+        barrier()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([e2e_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = B_PER_GPU * world * args.e2e_steps / (float(t.item()) * 1e-3)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
