@@ -9,11 +9,11 @@ constexpr int SEL_THREADS = 1024;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_STAGES = 3;
 constexpr int SEL_STAGE_BYTES = 65536;  // one 128x128 fp32 plane
-constexpr int SEL_CAP = 2048;           // per-CTA candidate buffer (64-bit keys)
-constexpr int SEL_MASK_WORDS = 1024;    // qualifying-pixel bitmask of one unit
+constexpr int SEL_CAP = 4096;           // per-CTA candidate buffer (64-bit keys)
+constexpr int SEL_MASK_WORDS = 512;     // qualifying-pixel bitmask of one unit
 constexpr int SEL_RW = 4;               // rows per warp work item
 constexpr int SEL_MAX_K = 1024;
-constexpr int SEL_FIN_MAX = 8192;       // finalize sort capacity (keys)
+constexpr int SEL_FIN_MAX = 8192;       // separate-finalize sort capacity (keys); the fused finalize uses SEL_CAP
 
 struct SelectPlan {
   int n_img, C, H, W, K;
@@ -25,6 +25,8 @@ struct SelectPlan {
   int max_slots;  // candidate segments an image can receive (<= CTAs overlapping it)
   int use_tma;
   int nms;
+  int clamp_one;  // order by min(score, 1): exct_decode clamps the NMS'd maps before _topk (decode.py:299-302)
+  int fused_finalize;  // last CTA of an image merges its segments inside stage 1
   long long P;    // planes = n_img * C
 };
 

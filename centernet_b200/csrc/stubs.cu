@@ -14,15 +14,4 @@ int cnb_exct_decode(const float *, const float *, const float *, const float *, 
                     int, int, float *, void *, size_t, void *) {
   CNB_STUB("cnb_exct_decode");
 }
-size_t cnb_dcnv2_workspace_bytes(int, int, int, int, int, int, int, int, int, int, int) { return 0; }
-int cnb_dcnv2_forward(const float *, const float *, const float *, const float *, const float *, float *, int, int,
-                      int, int, int, int, int, int, int, int, int, int, int, int, void *, size_t, void *) {
-  CNB_STUB("cnb_dcnv2_forward");
-}
-int cnb_dcnv2_backward(const float *, const float *, const float *, const float *, const float *, float *, float *,
-                       float *, float *, float *, int, int, int, int, int, int, int, int, int, int, int, int, int,
-                       int, void *, size_t, void *) {
-  CNB_STUB("cnb_dcnv2_backward");
-}
-
 }  // extern "C"

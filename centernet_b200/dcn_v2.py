@@ -1,0 +1,95 @@
+"""Mirror of src/lib/models/networks/DCNv2/dcn_v2.py: DCNv2, DCN (+ DCNv2Pooling / DCNPooling
+surface).  Parameter names (`weight`, `bias`, `conv_offset_mask.*`) match the reference so its
+checkpoints load unchanged."""
+import math
+
+import torch
+from torch import nn
+from torch.nn.modules.utils import _pair
+
+from .dcn_v2_func import DCNv2Function, DCNv2PoolingFunction
+
+
+class DCNv2(nn.Module):
+    """dcn_v2.py:14-41."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, deformable_groups=1):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = stride
+        self.padding = padding
+        self.dilation = dilation
+        self.deformable_groups = deformable_groups
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels, *self.kernel_size))
+        self.bias = nn.Parameter(torch.Tensor(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):   # dcn_v2.py:31-37
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+        self.bias.data.zero_()
+
+    def forward(self, input, offset, mask):
+        func = DCNv2Function(self.stride, self.padding, self.dilation, self.deformable_groups)
+        return func(input, offset, mask, self.weight, self.bias)
+
+
+class DCN(DCNv2):
+    """dcn_v2.py:44-70: DCNv2 + the zero-initialised offset/mask conv."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, deformable_groups=1):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, deformable_groups)
+        self.conv_offset_mask = nn.Conv2d(self.in_channels,
+                                          self.deformable_groups * 3 * self.kernel_size[0] * self.kernel_size[1],
+                                          kernel_size=self.kernel_size, stride=(self.stride, self.stride),
+                                          padding=(self.padding, self.padding), bias=True)
+        self.init_offset()
+
+    def init_offset(self):
+        self.conv_offset_mask.weight.data.zero_()
+        self.conv_offset_mask.bias.data.zero_()
+
+    def forward(self, input):
+        out = self.conv_offset_mask(input)
+        o1, o2, mask = torch.chunk(out, 3, dim=1)
+        offset = torch.cat((o1, o2), dim=1)
+        mask = torch.sigmoid(mask)
+        func = DCNv2Function(self.stride, self.padding, self.dilation, self.deformable_groups)
+        return func(input, offset, mask, self.weight, self.bias)
+
+
+class DCNv2Pooling(nn.Module):
+    """dcn_v2.py:73-106 (surface only; see DCNv2PoolingFunction)."""
+
+    def __init__(self, spatial_scale, pooled_size, output_dim, no_trans, group_size=1, part_size=None,
+                 sample_per_part=4, trans_std=.0):
+        super().__init__()
+        self.spatial_scale, self.pooled_size, self.output_dim, self.no_trans = spatial_scale, pooled_size, output_dim, no_trans
+        self.group_size = group_size
+        self.part_size = pooled_size if part_size is None else part_size
+        self.sample_per_part, self.trans_std = sample_per_part, trans_std
+        self.func = DCNv2PoolingFunction(spatial_scale, pooled_size, output_dim, no_trans, group_size, self.part_size,
+                                         sample_per_part, trans_std)
+
+    def forward(self, data, rois, offset):
+        if self.no_trans:
+            offset = data.new()
+        return self.func(data, rois, offset)
+
+
+class DCNPooling(DCNv2Pooling):
+    """dcn_v2.py:108-171 (surface only)."""
+
+    def __init__(self, spatial_scale, pooled_size, output_dim, no_trans, group_size=1, part_size=None,
+                 sample_per_part=4, trans_std=.0, deform_fc_dim=1024):
+        super().__init__(spatial_scale, pooled_size, output_dim, no_trans, group_size, part_size, sample_per_part,
+                         trans_std)
+        self.deform_fc_dim = deform_fc_dim
+
+    def forward(self, data, rois):
+        raise NotImplementedError("DCNPooling: deformable PSROI pooling is not implemented in centernet_b200")

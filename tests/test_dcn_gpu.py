@@ -1,0 +1,95 @@
+"""GPU parity for DCNv2 forward / backward (A10-A12) through the DCNv2Function / DCN mirrors.
+Forward <= 1e-4 abs vs the fp64 oracle (fp32-accurate mode); backward
+compared with autograd through the fp64 oracle at the gradcheck tolerances of DCNv2/test.py:90,115."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.dcn_ref import dcn_v2_forward
+
+pytestmark = pytest.mark.gpu
+
+
+def make(B, Ci, H, W, Co, dg, stride=1, seed=0, off_scale=2.0):
+    g = torch.Generator().manual_seed(seed)
+    Ho = (H + 2 - 3) // stride + 1
+    Wo = (W + 2 - 3) // stride + 1
+    x = torch.randn(B, Ci, H, W, generator=g)
+    off = torch.randn(B, 18 * dg, Ho, Wo, generator=g) * off_scale
+    m = torch.sigmoid(torch.randn(B, 9 * dg, Ho, Wo, generator=g))
+    w = torch.randn(Co, Ci, 3, 3, generator=g) / (3.0 * Ci ** 0.5)
+    b = torch.randn(Co, generator=g)
+    return x, off, m, w, b
+
+
+def test_zero_offset_identity_kat():
+    """DCNv2/test.py:32-65 (check_zero_offset) on the CUDA op."""
+    from centernet_b200.dcn_v2 import DCNv2
+    N, C, H, W = 2, 2, 4, 4
+    torch.manual_seed(0)
+    conv_offset = torch.zeros(N, 18, H, W, device="cuda")
+    conv_mask = torch.full((N, 9, H, W), 0.5, device="cuda")
+    dcn = DCNv2(C, C, (3, 3), stride=1, padding=1, dilation=1, deformable_groups=1).cuda()
+    dcn.weight.data.zero_()
+    dcn.bias.data.zero_()
+    for i in range(C):
+        dcn.weight.data[i, i, 1, 1] = 1.0
+    x = torch.randn(N, C, H, W, device="cuda")
+    out = dcn(x, conv_offset, conv_mask) * 2
+    assert (out - x).abs().max().item() < 1e-6
+
+
+SHAPES = [
+    # B, Cin, H, W, Cout, dg, stride
+    (2, 64, 32, 32, 64, 1, 1),     # dla_34 style 64->64
+    (1, 128, 16, 16, 128, 1, 1),   # Cout > 64 -> two accumulator sets
+    (2, 12, 9, 11, 5, 2, 1),       # odd sizes, 2 deformable groups, partial channel chunk
+    (2, 6, 10, 14, 7, 1, 2),       # stride 2
+    (1, 256, 8, 8, 64, 1, 1),      # deep reduction
+]
+
+
+@pytest.mark.parametrize("B,Ci,H,W,Co,dg,stride", SHAPES)
+def test_forward_vs_oracle(B, Ci, H, W, Co, dg, stride):
+    from centernet_b200.dcn_v2_func import DCNv2Function
+    x, off, m, w, b = make(B, Ci, H, W, Co, dg, stride)
+    want = dcn_v2_forward(x, off, m, w, b, stride, 1, 1, dg)
+    got = DCNv2Function(stride, 1, 1, dg)(x.cuda(), off.cuda(), m.cuda(), w.cuda(), b.cuda())
+    assert got.shape == want.shape
+    err = (got.double().cpu() - want).abs().max().item()
+    assert err <= 1e-4, err
+
+
+@pytest.mark.parametrize("B,Ci,H,W,Co,dg,stride", [(2, 16, 12, 12, 8, 1, 1), (1, 12, 9, 11, 5, 2, 1), (2, 6, 10, 14, 7, 1, 2),
+                                                    (1, 64, 16, 16, 64, 1, 1)])
+def test_backward_vs_oracle_autograd(B, Ci, H, W, Co, dg, stride):
+    from centernet_b200.dcn_v2_func import DCNv2Function
+    x, off, m, w, b = make(B, Ci, H, W, Co, dg, stride, seed=3, off_scale=1.3)
+    leaves = [t.clone().double().requires_grad_(True) for t in (x, off, m, w, b)]
+    out = dcn_v2_forward(*leaves, stride, 1, 1, dg)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(9), dtype=torch.float64)
+    (out * go).sum().backward()
+    cl = [t.clone().cuda().requires_grad_(True) for t in (x, off, m, w, b)]
+    got = DCNv2Function(stride, 1, 1, dg)(*cl)
+    (got * go.float().cuda()).sum().backward()
+    for name, a, r in zip(("input", "offset", "mask", "weight", "bias"), cl, leaves):
+        ref = r.grad
+        err = (a.grad.double().cpu() - ref).abs().max().item()
+        scale = max(1.0, ref.abs().max().item())
+        assert err <= 1e-3 * scale, (name, err, scale)      # fp32 gradcheck tolerance of test.py:115 (atol 1e-3)
+
+
+def test_dcn_module_and_state_dict_names():
+    from centernet_b200.dcn_v2 import DCN
+    dcn = DCN(16, 8, kernel_size=(3, 3), stride=1, padding=1, deformable_groups=1).cuda()
+    assert sorted(dcn.state_dict().keys()) == ["bias", "conv_offset_mask.bias", "conv_offset_mask.weight", "weight"]
+    x = torch.randn(2, 16, 20, 20, device="cuda", requires_grad=True)
+    y = dcn(x)
+    # zero-initialised offset conv: offsets 0, mask 0.5 -> equals 0.5 * conv2d(x, weight) + bias
+    ref = 0.5 * torch.nn.functional.conv2d(x, dcn.weight, None, 1, 1) + dcn.bias.view(1, -1, 1, 1)
+    assert (y - ref).abs().max().item() < 1e-4
+    y.sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all()
+    assert dcn.weight.grad is not None and dcn.conv_offset_mask.weight.grad is not None
+    with pytest.raises(NotImplementedError):
+        dcn.cpu()(torch.randn(1, 16, 8, 8))
