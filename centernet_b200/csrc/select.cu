@@ -248,19 +248,70 @@ __device__ __forceinline__ UnitGeom unit_geom(const SelectPlan &pl, long long p_
   return g;
 }
 
-// FAST: TMA path with a single 128-column block per row (W <= 128, W % 4 == 0).
-template <bool NMS, bool TMA, bool FAST>
+// ---- running threshold: 2-level histogram of the pushed scores (256 bins per octave over
+// [2^-16, 1), 64 coarse x 64 fine).  The lower edge of the highest bin whose suffix count reaches
+// K is a valid lower bound of the image's K-th best score: at least K real candidates lie above it.
+__device__ __forceinline__ int hist_bin(uint32_t bits) {
+  const int e = (int)(bits >> 15) - ((127 - 16) << 8);
+  return min(max(e, 0), SEL_HIST_FINE - 1);
+}
+__device__ __forceinline__ uint32_t bin_lower_bits(int b) {
+  return b <= 0 ? 1u : ((uint32_t)(b + ((127 - 16) << 8)) << 15);
+}
+// Highest of 64 bins whose suffix count is >= need (or -1); *rem = need - (count strictly above it).
+__device__ __forceinline__ int warp_suffix_pick(const int *bins, int lane, int need, int *rem) {
+  const int c0 = bins[2 * lane], c1 = bins[2 * lane + 1];
+  const int s = c0 + c1;
+  int suf = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += t;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, suf >= need);
+  if (!bal) return -1;
+  const int L = 31 - __clz(bal);
+  const int above = __shfl_sync(0xffffffffu, suf - s, L);
+  const int c1L = __shfl_sync(0xffffffffu, c1, L);
+  if (above + c1L >= need) {
+    *rem = need - above;
+    return 2 * L + 1;
+  }
+  *rem = need - above - c1L;
+  return 2 * L;
+}
+// warp 0 only
+__device__ __forceinline__ void update_threshold(const int *fine, const int *coarse, int lane, int K,
+                                                 uint32_t *s_thr) {
+  int rem = 0, rem2 = 0;
+  const int cb = warp_suffix_pick(coarse, lane, K, &rem);
+  uint32_t bits = 0u;
+  if (cb >= 0) {
+    const int fb = warp_suffix_pick(fine + cb * 64, lane, rem, &rem2);
+    bits = bin_lower_bits(cb * 64 + max(fb, 0));
+  }
+  if (lane == 0) *s_thr = bits;
+}
+
+// MODE 0: generic geometry; 1: one 128-column block per row (W <= 128, W % 4 == 0, TMA);
+// MODE 2: the hot geometry, whole 128x128 planes (4 rows per warp, fully unrolled).
+template <bool NMS, bool TMA, int MODE>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict__ cand,
                 int *__restrict__ cand_cnt, int *__restrict__ img_done, const FinalizeOut fout) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *stages = reinterpret_cast<float *>(smem_raw);
   u64 *buf = reinterpret_cast<u64 *>(smem_raw + (size_t)SEL_STAGES * SEL_STAGE_BYTES);
-  uint32_t *masks = reinterpret_cast<uint32_t *>(buf + SEL_CAP);
+  int *fine = reinterpret_cast<int *>(buf + SEL_CAP);
+  int *coarse = fine + SEL_HIST_FINE;
+  uint32_t *masks = reinterpret_cast<uint32_t *>(coarse + SEL_HIST_COARSE);
   uint64_t *full = reinterpret_cast<uint64_t *>(masks + SEL_MASK_WORDS);
-  int *s_cnt = reinterpret_cast<int *>(full + SEL_STAGES);  // [0] buffer count, [1] overflow flag, [2] last flag
+  // [0] buffer count, [1] overflow flag, [2] last-CTA flag, [3] compaction count, [4] threshold bits, [5] count at last update
+  int *s_cnt = reinterpret_cast<int *>(full + SEL_STAGES);
+  uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_cnt + 4);
   __shared__ int s_tmp[32];
   __shared__ u64 s_red[32];
+  constexpr bool FAST = (MODE >= 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = pl.H, W = pl.W, Wp = pl.Wp, ncb = pl.ncb, K = pl.K;
@@ -280,32 +331,58 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
     for (uint32_t off = 0; off < bytes; off += 16384u)
       bulk_g2s(dst + off, gsrc + off, min(16384u, bytes - off), &full[s]);
   };
-
-  if (tid == 0) {
-    s_cnt[0] = 0;
-    s_cnt[1] = 0;
-    s_cnt[2] = 0;
-    if (TMA) {
-      for (int s = 0; s < SEL_STAGES; ++s) mbar_init(&full[s], 1);
-      mbar_fence_init();
+  auto clear_hist = [&]() {
+    for (int i = tid; i < SEL_HIST_FINE + SEL_HIST_COARSE; i += SEL_THREADS) fine[i] = 0;  // coarse follows fine
+    if (tid == 0) {
+      s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[3] = 0; s_cnt[5] = 0;
+      *s_thr = 0u;
     }
+  };
+
+  if (tid == 0 && TMA) {
+    for (int s = 0; s < SEL_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
   }
+  clear_hist();
   __syncthreads();
   if (TMA && tid == 0) {
     for (int u = 0; u < SEL_STAGES && u < total_units; ++u) issue(u);
   }
 
-  u64 thr64 = 0ull;
+  u64 thr64 = 0ull;  // exact key threshold; non-zero only after a sort-prune (overflow fallback)
   int cur_img = -1;
 
   auto flush = [&](int img) {
-    cta_prune(buf, s_cnt, K);
-    const int n = min(s_cnt[0], K);
+    __syncthreads();
+    const int cnt = s_cnt[0];
+    const u64 *outp = buf;
+    int n_out = min(cnt, K);
+    if (cnt > K && cnt <= SEL_CAP / 2) {
+      // cut with the histogram threshold, sort only the survivors (>= K of them, see header)
+      if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+      __syncthreads();
+      const uint32_t tb = *s_thr;
+      u64 *hi = buf + SEL_CAP / 2;
+      for (int t = tid; t < cnt; t += SEL_THREADS) {
+        const u64 key = buf[t];
+        if (key_bits(key) >= tb) hi[atomicAdd(&s_cnt[3], 1)] = key;
+      }
+      __syncthreads();
+      const int m = s_cnt[3];
+      const int n = next_pow2(m);
+      for (int t = m + tid; t < n; t += SEL_THREADS) hi[t] = 0ull;
+      __syncthreads();
+      cta_sort_desc(hi, n);
+      outp = hi;
+      n_out = min(m, K);
+    } else {
+      cta_prune(buf, s_cnt, K);
+    }
     const int i0 = cta_of_plane((long long)img * pl.C, pl.P, pl.n_cta);
     const int slot = (int)blockIdx.x - i0;
     u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * K;
-    for (int t = tid; t < n; t += SEL_THREADS) dst[t] = buf[t];
-    if (tid == 0) cand_cnt[(size_t)img * pl.max_slots + slot] = n;
+    for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = outp[t];
+    if (tid == 0) cand_cnt[(size_t)img * pl.max_slots + slot] = n_out;
     if (pl.fused_finalize) {
       __threadfence();
       __syncthreads();
@@ -321,7 +398,7 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
       }
     }
     __syncthreads();
-    if (tid == 0) s_cnt[0] = 0;
+    clear_hist();
     __syncthreads();
   };
 
@@ -348,10 +425,42 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
     }
 
     // ---------------- phase A: peak + threshold test -> bitmask of qualifying pixels
-    // signed compare: negative floats are negative ints, +0 fails thr_s >= 1
-    const int thr_s = max((int)key_bits(thr64), 1);
+    // thr_f >= smallest positive float, so b == max(hmax, thr_f) also rejects b <= 0
+    const uint32_t thr_bits = max(max(*s_thr, key_bits(thr64)), 1u);
+    const float thr_f = __uint_as_float(thr_bits);
     const int rows = g.r1 - g.r0;
-    if (FAST) {
+    if (MODE == 2) {
+      // whole 128x128 plane: warp w owns rows 4w..4w+3, lane l columns 4l..4l+3
+      const int y0 = warp * 4;
+      const float *p = st + (size_t)y0 * 128 + lane * 4;
+      const float4 ninf = make_float4(NI, NI, NI, NI);
+      float4 r_[6];
+      r_[0] = (y0 > 0) ? *reinterpret_cast<const float4 *>(p - 128) : ninf;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r_[i + 1] = *reinterpret_cast<const float4 *>(p + i * 128);
+      r_[5] = (y0 + 4 < 128) ? *reinterpret_cast<const float4 *>(p + 4 * 128) : ninf;
+      uint4 *mrow = reinterpret_cast<uint4 *>(masks) + y0;
+      const bool first = (lane == 0), last = (lane == 31);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = r_[i], b = r_[i + 1], c = r_[i + 2];
+        const float v0 = fmax3(a.x, b.x, c.x), v1 = fmax3(a.y, b.y, c.y);
+        const float v2 = fmax3(a.z, b.z, c.z), v3 = fmax3(a.w, b.w, c.w);
+        float l = __shfl_up_sync(0xffffffffu, v3, 1);
+        float r = __shfl_down_sync(0xffffffffu, v0, 1);
+        l = first ? NI : l;
+        r = last ? NI : r;
+        const float m01 = fmaxf(v0, v1), m23 = fmaxf(v2, v3);
+        const bool q0 = (b.x == fmax3(l, m01, thr_f));
+        const bool q1 = (b.y == fmax3(m01, v2, thr_f));
+        const bool q2 = (b.z == fmax3(v1, m23, thr_f));
+        const bool q3 = (b.w == fmax3(m23, r, thr_f));
+        const uint32_t m0 = __ballot_sync(0xffffffffu, q0), m1 = __ballot_sync(0xffffffffu, q1);
+        const uint32_t m2 = __ballot_sync(0xffffffffu, q2), m3 = __ballot_sync(0xffffffffu, q3);
+        if (first) mrow[i] = make_uint4(m0, m1, m2, m3);
+      }
+    } else if (MODE == 1) {
+      const int thr_s = (int)thr_bits;
       const int rw = (rows + SEL_WARPS - 1) / SEL_WARPS;
       const int y0 = g.r0 + warp * rw, yend = min(y0 + rw, g.r1);
       if (y0 < yend) {
@@ -391,6 +500,7 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
         }
       }
     } else {
+      const int thr_s = (int)thr_bits;
       const int ngroups = (rows + SEL_RW - 1) / SEL_RW;
       for (int item = warp; item < ngroups * ncb; item += SEL_WARPS) {
         const int grp = item / ncb, cb = item - grp * ncb;
@@ -441,7 +551,7 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
       }
     }
 
-    // ---------------- phase B: expand bitmasks into the key buffer
+    // ---------------- phase B: expand bitmasks into the key buffer (+ histogram)
     const int words = rows * ncb * 4;
     const uint32_t cbase = (uint32_t)((long long)g.c * HW);
     auto make = [&](int word, int bit) -> u64 {
@@ -452,19 +562,23 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
       if (pl.clamp_one) v = fminf(v, 1.0f);
       return make_key(__float_as_uint(v), cbase + (uint32_t)(y * W + x));
     };
-    const bool boot = (thr64 == 0ull);
-    const int wpr = boot ? max((words + 3) >> 2, 32) : words;  // no threshold yet: quarter units
+    // while no threshold exists yet, expand an eighth of the unit at a time so it appears early
+    const int wpr = (*s_thr == 0u && thr64 == 0ull) ? max((words + 7) >> 3, 16) : words;
     for (int base = 0; base < words; base += wpr) {
       const int end = min(base + wpr, words);
-      __syncthreads();  // masks complete / previous round done
+      __syncthreads();  // masks complete / previous round (and its threshold update) done
       const int n0 = s_cnt[0];
+      const uint32_t tb = *s_thr;
       for (int t = base + tid; t < end; t += SEL_THREADS) {
         uint32_t m = masks[t];
         while (m) {
           const int bit = __ffs(m) - 1;
           m &= m - 1;
           const u64 key = make(t, bit);
-          if (key > thr64) {
+          if (key_bits(key) >= tb && key > thr64) {
+            const int hb = hist_bin(key_bits(key));
+            atomicAdd(&fine[hb], 1);      // every qualifying candidate is counted exactly once
+            atomicAdd(&coarse[hb >> 6], 1);
             const int slot = atomicAdd(&s_cnt[0], 1);
             if (slot < SEL_CAP) buf[slot] = key;
             else s_cnt[1] = 1;
@@ -473,8 +587,8 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
       }
       __syncthreads();
       if (s_cnt[1]) {
-        // overflow: drop this round's partial pushes and redo it in <=1024-candidate steps,
-        // pruning whenever a full step would not fit (K <= 1024 <= CAP - 1024 ... CAP/2)
+        // overflow: drop this round's partial pushes and redo it exactly, in <=1024-candidate steps,
+        // sort-pruning whenever a full step would not fit (K <= 1024 = CAP - 1024)
         __syncthreads();
         if (tid == 0) {
           s_cnt[0] = n0;
@@ -486,15 +600,17 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
           const int word = b2 + (tid >> 5);
           if (word < end && ((masks[word] >> (tid & 31)) & 1u)) {
             const u64 key = make(word, tid & 31);
-            if (key > thr64) buf[atomicAdd(&s_cnt[0], 1)] = key;
+            if (key_bits(key) >= tb && key > thr64) buf[atomicAdd(&s_cnt[0], 1)] = key;
           }
           __syncthreads();
         }
       }
-      const int cnt = s_cnt[0];
-      if (cnt > SEL_CAP / 2 || (thr64 == 0ull && cnt >= K && cnt >= 256)) thr64 = cta_prune(buf, s_cnt, K);
+      if (warp == 0 && s_cnt[0] != s_cnt[5]) {  // new candidates: refresh the running threshold
+        update_threshold(fine, coarse, lane, K, s_thr);
+        if (lane == 0) s_cnt[5] = s_cnt[0];
+      }
     }
-    __syncthreads();  // everyone is done with this stage and with the masks
+    __syncthreads();  // everyone is done with this stage, the masks and the threshold update
     // the stage is free again: prefetch the unit that will reuse it
     if (TMA && tid == 0 && u + SEL_STAGES < total_units) issue(u + SEL_STAGES);
   }
@@ -515,8 +631,8 @@ k_select_finalize(const float *__restrict__ src, const SelectPlan pl, const u64 
 
 // ------------------------------------------------------------------ host
 static size_t stage1_smem_bytes() {
-  return (size_t)SEL_STAGES * SEL_STAGE_BYTES + (size_t)SEL_CAP * 8 + (size_t)SEL_MASK_WORDS * 4 +
-         SEL_STAGES * 8 + 16;
+  return (size_t)SEL_STAGES * SEL_STAGE_BYTES + (size_t)SEL_CAP * 8 +
+         (size_t)(SEL_HIST_FINE + SEL_HIST_COARSE) * 4 + (size_t)SEL_MASK_WORDS * 4 + SEL_STAGES * 8 + 32;
 }
 
 int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, int nms, SelectPlan *pl) {
@@ -568,7 +684,7 @@ size_t select_workspace_bytes(const SelectPlan &pl) {
   return keys + cnts + done;
 }
 
-template <bool NMS, bool TMA, bool FAST>
+template <bool NMS, bool TMA, int MODE>
 static int launch_stage1(const float *src, const SelectPlan &pl, const FinalizeOut &out, u64 *cand, int *cnt,
                          int *done, cudaStream_t stream) {
   const size_t smem1 = stage1_smem_bytes();
@@ -576,11 +692,11 @@ static int launch_stage1(const float *src, const SelectPlan &pl, const FinalizeO
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    CNB_CUDA(cudaFuncSetAttribute(k_select_stage1<NMS, TMA, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CNB_CUDA(cudaFuncSetAttribute(k_select_stage1<NMS, TMA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem1));
     configured_dev = dev;
   }
-  k_select_stage1<NMS, TMA, FAST><<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, out);
+  k_select_stage1<NMS, TMA, MODE><<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, out);
   CNB_CHECK_LAUNCH("select stage 1");
   count_launch();
   return CNB_OK;
@@ -591,12 +707,14 @@ static int launch_select(const float *src, const SelectPlan &pl, const FinalizeO
                          int *done, cudaStream_t stream) {
   if (pl.fused_finalize) CNB_CUDA(cudaMemsetAsync(done, 0, (size_t)pl.n_img * 4, stream));
   int rc;
-  if (pl.use_tma && pl.ncb == 1)
-    rc = launch_stage1<NMS, true, true>(src, pl, out, cand, cnt, done, stream);
+  if (NMS && pl.use_tma && pl.W == 128 && pl.H == 128 && pl.rb == 128)
+    rc = launch_stage1<NMS, true, 2>(src, pl, out, cand, cnt, done, stream);
+  else if (pl.use_tma && pl.ncb == 1)
+    rc = launch_stage1<NMS, true, 1>(src, pl, out, cand, cnt, done, stream);
   else if (pl.use_tma)
-    rc = launch_stage1<NMS, true, false>(src, pl, out, cand, cnt, done, stream);
+    rc = launch_stage1<NMS, true, 0>(src, pl, out, cand, cnt, done, stream);
   else
-    rc = launch_stage1<NMS, false, false>(src, pl, out, cand, cnt, done, stream);
+    rc = launch_stage1<NMS, false, 0>(src, pl, out, cand, cnt, done, stream);
   if (rc != CNB_OK) return rc;
   if (!pl.fused_finalize) {
     const size_t smem2 = (size_t)next_pow2(pl.max_slots * pl.K > pl.K ? pl.max_slots * pl.K : pl.K) * 8;
