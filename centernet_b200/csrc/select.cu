@@ -39,10 +39,25 @@ __host__ __device__ __forceinline__ int cta_of_plane(long long p, long long P, i
   return (int)(((p + 1) * (long long)n_cta - 1) / P);
 }
 
-// ------------------------------------------------------------------ CTA-wide bitonic sort
-// Sorts buf[0..n) descending; n is a power of two; all threads of the CTA must call.
-__device__ __forceinline__ void cta_sort_desc(u64 *buf, int n) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+// ------------------------------------------------------------------ cooperating-thread groups
+// The helpers below run either on the whole CTA (generic kernel, separate finalize kernel) or on a
+// single warp (the warp-asynchronous hot kernel, where one warp at a time owns the selection state).
+struct CtaGroup {
+  static __device__ __forceinline__ int tid() { return threadIdx.x; }
+  static __device__ __forceinline__ int n() { return blockDim.x; }
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+struct WarpGroup {
+  static __device__ __forceinline__ int tid() { return threadIdx.x & 31; }
+  static __device__ __forceinline__ int n() { return 32; }
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+// ------------------------------------------------------------------ bitonic sort
+// Sorts buf[0..n) descending; n is a power of two; all threads of the group must call.
+template <typename G>
+__device__ __forceinline__ void group_sort_desc(u64 *buf, int n) {
+  const int tid = G::tid(), nt = G::n();
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = tid; t < (n >> 1); t += nt) {
@@ -54,10 +69,11 @@ __device__ __forceinline__ void cta_sort_desc(u64 *buf, int n) {
           buf[i + j] = a;
         }
       }
-      __syncthreads();
+      G::sync();
     }
   }
 }
+__device__ __forceinline__ void cta_sort_desc(u64 *buf, int n) { group_sort_desc<CtaGroup>(buf, n); }
 
 __host__ __device__ __forceinline__ int next_pow2(int v) {
   int n = 2;
@@ -67,20 +83,22 @@ __host__ __device__ __forceinline__ int next_pow2(int v) {
 
 // Sort the candidate buffer and keep the K best.  Returns the new 64-bit threshold
 // (key of the K-th best, or 0 when fewer than K are known).  CTA-uniform.
-__device__ __forceinline__ u64 cta_prune(u64 *buf, int *s_cnt, int K) {
-  __syncthreads();
-  const int cnt = *s_cnt;
+template <typename G>
+__device__ __forceinline__ u64 group_prune(u64 *buf, int *s_cnt, int K) {
+  G::sync();
+  const int cnt = *(volatile int *)s_cnt;
   const int n = next_pow2(cnt);
-  for (int t = cnt + threadIdx.x; t < n; t += blockDim.x) buf[t] = 0ull;
-  __syncthreads();
-  cta_sort_desc(buf, n);
+  for (int t = cnt + G::tid(); t < n; t += G::n()) buf[t] = 0ull;
+  G::sync();
+  group_sort_desc<G>(buf, n);
   u64 thr = 0ull;
   if (cnt >= K) thr = buf[K - 1];
-  __syncthreads();
-  if (threadIdx.x == 0 && cnt > K) *s_cnt = K;
-  __syncthreads();
+  G::sync();
+  if (G::tid() == 0 && cnt > K) *s_cnt = K;
+  G::sync();
   return thr;
 }
+__device__ __forceinline__ u64 cta_prune(u64 *buf, int *s_cnt, int K) { return group_prune<CtaGroup>(buf, s_cnt, K); }
 
 // ------------------------------------------------------------------ finalize (shared by both paths)
 // v'(i): the reference's heat*keep value of flat pixel i (keep only in NMS mode).
@@ -105,22 +123,22 @@ __device__ __forceinline__ float nms_value(const float *__restrict__ img, int C,
   return (m == v) ? v : 0.0f;
 }
 
-template <bool NMS>
+template <bool NMS, typename G>
 __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &pl, u64 *sbuf, int have, int K,
                               int *s_tmp, u64 *s_red) {
   // Need K-have more entries ranked (value desc, index asc) among NON-positive v'.
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int tid = G::tid(), lane = tid & 31, warp = tid >> 5, nw = G::n() >> 5;
   const long long N = (long long)pl.C * pl.H * pl.W;
   int found = 0;
   const int need = K - have;
   // step 1: zeros, in index order
-  for (long long base = 0; base < N && found < need; base += blockDim.x) {
+  for (long long base = 0; base < N && found < need; base += G::n()) {
     const long long i = base + tid;
     bool pred = false;
     if (i < N) pred = (nms_value<NMS>(img, pl.C, pl.H, pl.W, i) == 0.0f);
     const uint32_t bal = __ballot_sync(0xffffffffu, pred);
     if (lane == 0) s_tmp[warp] = __popc(bal);
-    __syncthreads();
+    G::sync();
     int before = 0, total = 0;
     for (int w2 = 0; w2 < nw; ++w2) {
       const int cw = s_tmp[w2];
@@ -130,14 +148,14 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
     const int pos = found + before + __popc(bal & ((1u << lane) - 1u));
     if (pred && pos < need) sbuf[have + pos] = make_key(0u, (uint32_t)i);
     found += total;
-    __syncthreads();
+    G::sync();
   }
   found = min(found, need);
   // step 2: negative values, largest first (brute force; pathological inputs only)
   u64 prev = ~0ull;
   while (found < need) {
     u64 best = 0ull;
-    for (long long i = tid; i < N; i += blockDim.x) {
+    for (long long i = tid; i < N; i += G::n()) {
       const float v = nms_value<NMS>(img, pl.C, pl.H, pl.W, i);
       if (v < 0.0f) {
         const u64 key = ((u64)(~__float_as_uint(v)) << 32) | (u64)(0xffffffffu - (uint32_t)i);
@@ -149,10 +167,10 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
       best = other > best ? other : best;
     }
     if (lane == 0) s_red[warp] = best;
-    __syncthreads();
+    G::sync();
     best = 0ull;
     for (int w2 = 0; w2 < nw; ++w2) best = s_red[w2] > best ? s_red[w2] : best;
-    __syncthreads();
+    G::sync();
     if (best == 0ull) {  // nothing left (NaNs only): pad with pixel 0 / score 0
       if (tid == 0) sbuf[have + found] = make_key(0u, 0u);
     } else {
@@ -161,35 +179,35 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
     }
     ++found;
   }
-  __syncthreads();
+  G::sync();
 }
 
 // Merge the segments of image b (written by the stage-1 CTAs i0..i1), sort, emit.
 // sbuf must hold next_pow2(max(max_slots*K, K)) keys.  All threads of the CTA call.
-template <bool NMS>
+template <bool NMS, typename G>
 __device__ void finalize_image(const float *__restrict__ src, const SelectPlan &pl, int b,
                                const u64 *__restrict__ cand, const int *__restrict__ cand_cnt,
                                const FinalizeOut &out, u64 *sbuf, int *s_tmp, u64 *s_red) {
-  const int tid = threadIdx.x, K = pl.K;
+  const int tid = G::tid(), K = pl.K;
   const int i0 = cta_of_plane((long long)b * pl.C, pl.P, pl.n_cta);
   const int i1 = cta_of_plane((long long)(b + 1) * pl.C - 1, pl.P, pl.n_cta);
   int total = 0;
   for (int slot = 0; slot <= i1 - i0; ++slot) {
     const int n = __ldcg(cand_cnt + (size_t)b * pl.max_slots + slot);
     const u64 *seg = cand + ((size_t)b * pl.max_slots + slot) * K;
-    for (int t = tid; t < n; t += blockDim.x) sbuf[total + t] = __ldcg(seg + t);
+    for (int t = tid; t < n; t += G::n()) sbuf[total + t] = __ldcg(seg + t);
     total += n;
   }
   const int n = next_pow2(max(total, K));
-  for (int t = total + tid; t < n; t += blockDim.x) sbuf[t] = 0ull;
-  __syncthreads();
-  if (i1 > i0) cta_sort_desc(sbuf, n);  // a single segment arrives sorted already
+  for (int t = total + tid; t < n; t += G::n()) sbuf[t] = 0ull;
+  G::sync();
+  if (i1 > i0) group_sort_desc<G>(sbuf, n);  // a single segment arrives sorted already
   if (total < K) {
     const long long N = (long long)pl.C * pl.H * pl.W;
-    finalize_fill<NMS>(src + (long long)b * N, pl, sbuf, total, K, s_tmp, s_red);
+    finalize_fill<NMS, G>(src + (long long)b * N, pl, sbuf, total, K, s_tmp, s_red);
   }
   const long long HW = (long long)pl.H * pl.W;
-  for (int k = tid; k < K; k += blockDim.x) {
+  for (int k = tid; k < K; k += G::n()) {
     const u64 key = sbuf[k];
     const float score = __uint_as_float(key_bits(key));
     const uint32_t flat = key_idx(key);
@@ -224,7 +242,7 @@ __device__ void finalize_image(const float *__restrict__ src, const SelectPlan &
       d[5] = (float)cls;
     }
   }
-  __syncthreads();
+  G::sync();
 }
 
 // ------------------------------------------------------------------ stage 1
@@ -248,15 +266,15 @@ __device__ __forceinline__ UnitGeom unit_geom(const SelectPlan &pl, long long p_
   return g;
 }
 
-// ---- running threshold: 2-level histogram of the pushed scores (256 bins per octave over
-// [2^-16, 1), 64 coarse x 64 fine).  The lower edge of the highest bin whose suffix count reaches
+// ---- running threshold: 2-level histogram of the pushed scores (128 bins per octave over
+// [2^-16, 1), 32 coarse x 64 fine).  The lower edge of the highest bin whose suffix count reaches
 // K is a valid lower bound of the image's K-th best score: at least K real candidates lie above it.
 __device__ __forceinline__ int hist_bin(uint32_t bits) {
-  const int e = (int)(bits >> 15) - ((127 - 16) << 8);
+  const int e = (int)(bits >> 16) - ((127 - 16) << 7);
   return min(max(e, 0), SEL_HIST_FINE - 1);
 }
 __device__ __forceinline__ uint32_t bin_lower_bits(int b) {
-  return b <= 0 ? 1u : ((uint32_t)(b + ((127 - 16) << 8)) << 15);
+  return b <= 0 ? 1u : ((uint32_t)(b + ((127 - 16) << 7)) << 16);
 }
 // Highest of 64 bins whose suffix count is >= need (or -1); *rem = need - (count strictly above it).
 __device__ __forceinline__ int warp_suffix_pick(const int *bins, int lane, int need, int *rem) {
@@ -394,7 +412,7 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
       __syncthreads();
       if (s_cnt[2]) {  // every segment of this image is in global memory: merge + emit here
         __threadfence();
-        finalize_image<NMS>(src, pl, img, cand, cand_cnt, fout, buf, s_tmp, s_red);
+        finalize_image<NMS, CtaGroup>(src, pl, img, cand, cand_cnt, fout, buf, s_tmp, s_red);
       }
     }
     __syncthreads();
@@ -617,6 +635,281 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
   if (cur_img >= 0) flush(cur_img);
 }
 
+// ------------------------------------------------------------------ stage 1, hot geometry, warp-asynchronous
+// Whole 128x128 planes, TMA, NMS, fused finalize.  Within an image there is NO CTA-wide barrier:
+//   * every warp waits for the plane (mbarrier), sweeps its 4 rows (phase A) and pushes its own
+//     qualifying pixels straight from registers into the shared key buffer + histogram (atomics;
+//     ~20-100 pushes per plane in steady state), then arrives on sdone[stage];
+//   * warp (u mod 32) additionally refreshes the histogram threshold and, once all 32 warps have
+//     arrived for unit u, re-arms the stage with the TMA load of unit u+3.
+// Warps therefore drift apart by up to the depth of the stage ring and hide each other's latencies.
+// CTA barriers exist only at image boundaries (<= 2 per CTA at B=64): flush + ticket + finalize are
+// CTA-parallel there, and the first unit of an image is bootstrapped in two steps (16 rows first)
+// so a threshold exists before the bulk of the plane is pushed.  If the key buffer ever overflows
+// (plateaus, very dense peaks) the CTA re-derives its segment of that image exactly from global
+// memory at flush time (slow path, sort-prune).
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict__ cand, int *__restrict__ cand_cnt,
+             int *__restrict__ img_done, const FinalizeOut fout) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *stages = reinterpret_cast<float *>(smem_raw);
+  u64 *buf = reinterpret_cast<u64 *>(smem_raw + (size_t)SEL_STAGES * SEL_STAGE_BYTES);
+  int *fine = reinterpret_cast<int *>(buf + SEL_CAP);
+  int *coarse = fine + SEL_HIST_FINE;
+  uint32_t *unused_masks = reinterpret_cast<uint32_t *>(coarse + SEL_HIST_COARSE);
+  uint64_t *full = reinterpret_cast<uint64_t *>(unused_masks + SEL_MASK_WORDS);
+  int *s_cnt = reinterpret_cast<int *>(full + SEL_STAGES);   // [0] count [1] overflow [2] last flag [3] compaction
+  uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_cnt + 4);
+  __shared__ __align__(8) uint64_t sdone[SEL_STAGES];        // 32 warp arrivals: stage consumed
+  __shared__ int s_flag[4];                                  // compaction rendezvous requested for unit (u & 3)
+  __shared__ int s_tmp[32];
+  __shared__ u64 s_red[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = pl.K, C = pl.C;
+  constexpr int HW = 128 * 128;
+  const long long p_begin = cta_first_plane(blockIdx.x, pl.P, pl.n_cta);
+  const long long p_end = cta_first_plane(blockIdx.x + 1, pl.P, pl.n_cta);
+  const int total_units = (int)(p_end - p_begin);
+  const float NI = CNB_NEG_INF;
+
+  auto issue = [&](int u) {  // one lane
+    const int s = u % SEL_STAGES;
+    const char *gsrc = reinterpret_cast<const char *>(src + (p_begin + u) * (long long)HW);
+    char *dst = reinterpret_cast<char *>(stages) + (size_t)s * SEL_STAGE_BYTES;
+    mbar_expect_tx(&full[s], (uint32_t)SEL_STAGE_BYTES);
+#pragma unroll
+    for (uint32_t off = 0; off < (uint32_t)SEL_STAGE_BYTES; off += 16384u)
+      bulk_g2s(dst + off, gsrc + off, 16384u, &full[s]);
+  };
+  auto reset_state = [&]() {  // all threads, followed by a barrier at the call site
+    for (int i = tid; i < SEL_HIST_FINE + SEL_HIST_COARSE; i += SEL_THREADS) fine[i] = 0;
+    if (tid == 0) {
+      s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
+      *s_thr = 0u;
+    }
+  };
+
+  if (tid == 0) {
+    s_flag[0] = s_flag[1] = s_flag[2] = s_flag[3] = 0;
+    for (int s = 0; s < SEL_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&sdone[s], SEL_WARPS);
+    }
+    mbar_fence_init();
+  }
+  reset_state();
+  __syncthreads();
+  if (tid == 0) {
+    for (int u = 0; u < SEL_STAGES && u < total_units; ++u) issue(u);
+  }
+
+  // push one qualifying pixel (any lane of any warp, concurrently)
+  auto push = [&](float v, uint32_t flat) {
+    if (pl.clamp_one) v = fminf(v, 1.0f);
+    const uint32_t bits = __float_as_uint(v);
+    const int hb = hist_bin(bits);
+    atomicAdd(&fine[hb], 1);
+    atomicAdd(&coarse[hb >> 6], 1);
+    const int slot = atomicAdd(&s_cnt[0], 1);
+    if (slot < SEL_CAP) buf[slot] = make_key(bits, flat);
+    else s_cnt[1] = 1;
+  };
+
+  // ---- CTA-wide flush of image `img` (all threads; called at image boundaries only)
+  auto flush = [&](int img) {
+    __syncthreads();
+    const u64 *outp = buf;
+    int n_out;
+    if (s_cnt[1]) {
+      // the buffer overflowed at some point: rebuild this CTA's segment exactly from global memory
+      __syncthreads();
+      if (tid == 0) s_cnt[0] = 0;
+      __syncthreads();
+      u64 thr64 = 0ull;
+      const long long lo = max(p_begin, (long long)img * C), hi = min(p_end, (long long)(img + 1) * C);
+      const float *ibase = src + (long long)img * C * HW;
+      for (long long p = lo; p < hi; ++p) {
+        const int c = (int)(p - (long long)img * C);
+        for (int base = 0; base < HW; base += SEL_THREADS) {
+          if (s_cnt[0] + SEL_THREADS > SEL_CAP) thr64 = cta_prune(buf, s_cnt, K);
+          const long long flat = (long long)c * HW + base + tid;
+          float v = nms_value<true>(ibase, C, 128, 128, flat);
+          if (pl.clamp_one) v = fminf(v, 1.0f);
+          if (v > 0.0f) {
+            const u64 key = make_key(__float_as_uint(v), (uint32_t)flat);
+            if (key > thr64) buf[atomicAdd(&s_cnt[0], 1)] = key;
+          }
+          __syncthreads();
+        }
+      }
+      cta_prune(buf, s_cnt, K);
+      n_out = min(s_cnt[0], K);
+    } else {
+      const int cnt = s_cnt[0];
+      n_out = min(cnt, K);
+      if (cnt > K && cnt <= SEL_CAP / 2) {
+        if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+        __syncthreads();
+        const uint32_t tb = *s_thr;
+        u64 *hi = buf + SEL_CAP / 2;
+        for (int t = tid; t < cnt; t += SEL_THREADS) {
+          const u64 key = buf[t];
+          if (key_bits(key) >= tb) hi[atomicAdd(&s_cnt[3], 1)] = key;
+        }
+        __syncthreads();
+        const int m = s_cnt[3];
+        const int n = next_pow2(m);
+        for (int t = m + tid; t < n; t += SEL_THREADS) hi[t] = 0ull;
+        __syncthreads();
+        cta_sort_desc(hi, n);
+        outp = hi;
+        n_out = min(m, K);
+      } else {
+        cta_prune(buf, s_cnt, K);
+      }
+    }
+    const int i0 = cta_of_plane((long long)img * C, pl.P, pl.n_cta);
+    const int slot = (int)blockIdx.x - i0;
+    u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * K;
+    for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = outp[t];
+    if (tid == 0) cand_cnt[(size_t)img * pl.max_slots + slot] = n_out;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int i1 = cta_of_plane((long long)(img + 1) * C - 1, pl.P, pl.n_cta);
+      s_cnt[2] = (atomicAdd(&img_done[img], 1) == i1 - i0) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_cnt[2]) {  // every segment of this image is in global memory: merge + emit here
+      __threadfence();
+      finalize_image<true, CtaGroup>(src, pl, img, cand, cand_cnt, fout, buf, s_tmp, s_red);
+    }
+    __syncthreads();
+    reset_state();
+    __syncthreads();
+  };
+
+  // ---- phase A + push of rows [y0, y0 + 4) of the plane in stage `st`
+  const bool first = (lane == 0), lastl = (lane == 31);
+  auto sweep = [&](const float *st, int c, bool use_thr) {
+    const int y0 = warp * 4;
+    const float *p = st + (size_t)y0 * 128 + lane * 4;
+    const float4 ninf = make_float4(NI, NI, NI, NI);
+    float4 r_[6];
+    r_[0] = (y0 > 0) ? *reinterpret_cast<const float4 *>(p - 128) : ninf;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r_[i + 1] = *reinterpret_cast<const float4 *>(p + i * 128);
+    r_[5] = (y0 + 4 < 128) ? *reinterpret_cast<const float4 *>(p + 4 * 128) : ninf;
+    const uint32_t fbase = (uint32_t)c * (uint32_t)HW + (uint32_t)(y0 * 128 + lane * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // the running threshold is re-read per row (one broadcast LDS): fresher = fewer pushes
+      const float thr_f = __uint_as_float(max(use_thr ? *(volatile uint32_t *)s_thr : 0u, 1u));
+      const float4 a = r_[i], b = r_[i + 1], cc = r_[i + 2];
+      const float v0 = fmax3(a.x, b.x, cc.x), v1 = fmax3(a.y, b.y, cc.y);
+      const float v2 = fmax3(a.z, b.z, cc.z), v3 = fmax3(a.w, b.w, cc.w);
+      float l = __shfl_up_sync(0xffffffffu, v3, 1);
+      float r = __shfl_down_sync(0xffffffffu, v0, 1);
+      l = first ? NI : l;
+      r = lastl ? NI : r;
+      const float m01 = fmaxf(v0, v1), m23 = fmaxf(v2, v3);
+      const bool q0 = (b.x == fmax3(l, m01, thr_f));
+      const bool q1 = (b.y == fmax3(m01, v2, thr_f));
+      const bool q2 = (b.z == fmax3(v1, m23, thr_f));
+      const bool q3 = (b.w == fmax3(m23, r, thr_f));
+      if (q0 | q1 | q2 | q3) {  // rare: a few pixels per plane once the threshold exists
+        const uint32_t f = fbase + (uint32_t)(i * 128);
+        if (q0) push(b.x, f);
+        if (q1) push(b.y, f + 1);
+        if (q2) push(b.z, f + 2);
+        if (q3) push(b.w, f + 3);
+      }
+    }
+  };
+
+  // ---- CTA-wide compaction of the key buffer against the current threshold (rendezvous, rare)
+  auto compact = [&](int slot_idx) {
+    __syncthreads();
+    if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+    __syncthreads();
+    const uint32_t tb = *s_thr;
+    const int cnt = min(s_cnt[0], SEL_CAP);
+    u64 mine[SEL_CAP / SEL_THREADS];
+#pragma unroll
+    for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j) {
+      const int t = tid + j * SEL_THREADS;
+      mine[j] = (t < cnt) ? buf[t] : 0ull;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (s_cnt[0] <= SEL_CAP) s_cnt[0] = 0;   // an overflowed buffer stays flagged; flush rescans
+      s_flag[slot_idx] = 0;
+    }
+    __syncthreads();
+    if (s_cnt[0] == 0) {
+#pragma unroll
+      for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j)
+        if (mine[j] != 0ull && key_bits(mine[j]) >= tb) buf[atomicAdd(&s_cnt[0], 1)] = mine[j];
+    }
+    __syncthreads();
+  };
+
+  int img = (int)(p_begin / C), c = (int)(p_begin - (long long)img * C);
+  int stage = 0, par = 0;
+  bool fresh = true;  // first unit of an image in this CTA (CTA-uniform)
+  for (int u = 0; u < total_units; ++u) {
+    const float *st = stages + (size_t)stage * (SEL_STAGE_BYTES / 4);
+    mbar_wait(&full[stage], (uint32_t)par);
+    if (*(volatile int *)&s_flag[u & 3]) compact(u & 3);   // set 3 units ago, before this plane's TMA was issued
+    if (fresh) {
+      // bootstrap in three steps (rows 0-15, 16-47, 48-127), refreshing the threshold in between,
+      // so only ~600 of a dense plane's ~1800 peaks are ever pushed
+      if (warp < 4) sweep(st, c, false);
+      __syncthreads();
+      if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+      __syncthreads();
+      if (warp >= 4 && warp < 12) sweep(st, c, true);
+      __syncthreads();
+      if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+      __syncthreads();
+      if (warp >= 12) sweep(st, c, true);
+      __syncthreads();
+      if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+      __syncthreads();
+      fresh = false;
+    } else {
+      sweep(st, c, true);
+    }
+    __syncwarp();
+    if (first) mbar_arrive(&sdone[stage]);
+    if (warp == (u & (SEL_WARPS - 1))) {
+      update_threshold(fine, coarse, lane, K, s_thr);       // partial histograms give valid bounds too
+      mbar_wait(&sdone[stage], (uint32_t)par);                // all 32 warps are done with this stage
+      if (first && u + SEL_STAGES < total_units) {
+        // buffer half full: ask every warp to rendezvous at unit u+3 (nobody can start it before
+        // the TMA below is issued, so all of them will see the flag)
+        if (*(volatile int *)&s_cnt[0] > SEL_CAP / 2) s_flag[(u + SEL_STAGES) & 3] = 1;
+        issue(u + SEL_STAGES);
+      }
+    }
+    // next unit
+    if (++c == C) {
+      flush(img);
+      c = 0;
+      ++img;
+      fresh = true;
+    } else if (u == total_units - 1) {
+      flush(img);
+    }
+    if (++stage == SEL_STAGES) { stage = 0; par ^= 1; }
+  }
+}
+
 // ------------------------------------------------------------------ separate finalize kernel
 template <bool NMS>
 __global__ void __launch_bounds__(1024, 1)
@@ -626,7 +919,7 @@ k_select_finalize(const float *__restrict__ src, const SelectPlan pl, const u64 
   u64 *sbuf = reinterpret_cast<u64 *>(fin_raw);
   __shared__ int s_tmp[32];
   __shared__ u64 s_red[32];
-  finalize_image<NMS>(src, pl, blockIdx.x, cand, cand_cnt, out, sbuf, s_tmp, s_red);
+  finalize_image<NMS, CtaGroup>(src, pl, blockIdx.x, cand, cand_cnt, out, sbuf, s_tmp, s_red);
 }
 
 // ------------------------------------------------------------------ host
@@ -707,7 +1000,20 @@ static int launch_select(const float *src, const SelectPlan &pl, const FinalizeO
                          int *done, cudaStream_t stream) {
   if (pl.fused_finalize) CNB_CUDA(cudaMemsetAsync(done, 0, (size_t)pl.n_img * 4, stream));
   int rc;
-  if (NMS && pl.use_tma && pl.W == 128 && pl.H == 128 && pl.rb == 128)
+  if (NMS && pl.use_tma && pl.W == 128 && pl.H == 128 && pl.rb == 128 && pl.fused_finalize && pl.K <= 256) {
+    const size_t smem1 = stage1_smem_bytes();
+    static thread_local int hot_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (hot_dev != dev) {
+      CNB_CUDA(cudaFuncSetAttribute(k_select_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      hot_dev = dev;
+    }
+    k_select_hot<<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, out);
+    CNB_CHECK_LAUNCH("select stage 1 (hot)");
+    count_launch();
+    rc = CNB_OK;
+  } else if (NMS && pl.use_tma && pl.W == 128 && pl.H == 128 && pl.rb == 128)
     rc = launch_stage1<NMS, true, 2>(src, pl, out, cand, cnt, done, stream);
   else if (pl.use_tma && pl.ncb == 1)
     rc = launch_stage1<NMS, true, 1>(src, pl, out, cand, cnt, done, stream);

@@ -10,8 +10,8 @@ constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_STAGES = 3;
 constexpr int SEL_STAGE_BYTES = 65536;  // one 128x128 fp32 plane
 constexpr int SEL_CAP = 2048;           // per-CTA candidate buffer (64-bit keys)
-constexpr int SEL_HIST_FINE = 4096;     // running-threshold histogram: 256 bins per octave over [2^-16, 1)
-constexpr int SEL_HIST_COARSE = 64;
+constexpr int SEL_HIST_FINE = 2048;     // running-threshold histogram: 128 bins per octave over [2^-16, 1)
+constexpr int SEL_HIST_COARSE = 64;      // 64 fine bins each (only the first FINE/64 are used)
 constexpr int SEL_MASK_WORDS = 512;     // qualifying-pixel bitmask of one unit
 constexpr int SEL_RW = 4;               // rows per warp work item
 constexpr int SEL_MAX_K = 1024;

@@ -201,3 +201,71 @@ def test_error_behaviour():
         D.ctdet_decode(heat, torch.rand(1, 2, 8, 8, device="cuda"), K=65)
     with pytest.raises(RuntimeError):
         D.ctdet_decode(heat, torch.rand(1, 3, 8, 8, device="cuda"), K=4)
+
+
+def test_golden_exct():
+    from centernet_b200 import decode as D
+    g = golden("exct")
+    K, ND = int(g["K"]), int(g["num_dets"])
+    maps = dev(g["t"], g["l"], g["b"], g["r"], g["ct"])
+    regs = dev(g["t_regr"], g["l_regr"], g["b_regr"], g["r_regr"])
+    got = D.exct_decode(*maps, *regs, K=K, num_dets=ND).cpu().numpy()
+    assert_dets_equal(g["dets"], got, atol=TOL, positive_only=True, what="exct")
+    got = D.exct_decode(*maps, K=K, num_dets=ND).cpu().numpy()
+    assert_dets_equal(g["dets_noreg"], got, atol=TOL, positive_only=True, what="exct_noreg")
+    got = D.exct_decode(*maps, *regs, K=K, num_dets=ND, aggr_weight=0.1).cpu().numpy()
+    assert_dets_equal(g["dets_aggr"], got, atol=TOL, positive_only=True, what="exct_aggr")
+    agn_maps = dev(g["t1"], g["l1"], g["b1"], g["r1"], g["ct"])
+    got = D.agnex_ct_decode(*agn_maps, *regs, K=K, num_dets=ND).cpu().numpy()
+    assert_dets_equal(g["dets_agn"], got, atol=TOL, positive_only=True, what="agnex")
+
+
+def _extreme_maps(B, C, H, W, seed, n_obj=8):
+    """Structured t/l/b/r/centre maps: boxes whose extreme points and centre carry peaks of one class."""
+    rng = np.random.default_rng(seed)
+    base = (0.03 * rng.random((5, B, C, H, W))).astype(np.float32)
+    for b in range(B):
+        for _ in range(n_obj):
+            c = rng.integers(0, C)
+            x0, x1 = sorted(rng.integers(2, W - 2, 2)); y0, y1 = sorted(rng.integers(2, H - 2, 2))
+            if x1 - x0 < 4 or y1 - y0 < 4:
+                continue
+            tx, bx = rng.integers(x0, x1 + 1, 2); ly, ry = rng.integers(y0, y1 + 1, 2)
+            sc = rng.uniform(0.3, 0.95, 5).astype(np.float32)
+            base[0, b, c, y0, tx] = sc[0]; base[1, b, c, ly, x0] = sc[1]
+            base[2, b, c, y1, bx] = sc[2]; base[3, b, c, ry, x1] = sc[3]
+            base[4, b, c, (y0 + y1) // 2, (x0 + x1) // 2] = sc[4]
+    return [base[i] for i in range(5)]
+
+
+@pytest.mark.parametrize("B,C,H,W,K,ND,aggr", [(2, 6, 48, 64, 12, 300, 0.0), (1, 80, 128, 128, 20, 1000, 0.0),
+                                               (2, 3, 32, 40, 9, 200, 0.1)])
+def test_exct_vs_oracle(B, C, H, W, K, ND, aggr):
+    """Exact agreement with the oracle on EVERY row (the oracle and the kernel share the tie rule:
+    score desc, tuple index asc), including the non-positive filler rows."""
+    from centernet_b200 import decode as D
+    maps = _extreme_maps(B, C, H, W, 40 + K)
+    regs = [rnd((B, 2, H, W), 50 + i) for i in range(4)]
+    want = O.exct_decode(*maps, *regs, K=K, num_dets=ND, aggr_weight=aggr)
+    got = D.exct_decode(*dev(*maps), *dev(*regs), K=K, num_dets=ND, aggr_weight=aggr).cpu().numpy()
+    assert got.shape == (B, ND, 14)
+    assert (want[..., 4] > 0).sum() > 0
+    np.testing.assert_array_equal(got[..., 4], want[..., 4])
+    np.testing.assert_array_equal(got[..., 13], want[..., 13])
+    np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
+    # class-agnostic variant
+    t1, l1, b1, r1 = [m.max(axis=1, keepdims=True) for m in maps[:4]]
+    want = O.agnex_ct_decode(t1, l1, b1, r1, maps[4], *regs, K=K, num_dets=ND, aggr_weight=aggr)
+    got = D.agnex_ct_decode(*dev(t1, l1, b1, r1, maps[4]), *dev(*regs), K=K, num_dets=ND, aggr_weight=aggr).cpu().numpy()
+    np.testing.assert_array_equal(got[..., 4], want[..., 4])
+    np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
+
+
+def test_topk_nonpositive_scores():
+    from centernet_b200 import decode as D
+    scores = -noise(2, 3, 12, 16, 31)                       # every score negative, no peak test
+    scores[0, 1, 3, 3] = 0.0; scores[1, 2, 0, 0] = 0.25
+    want = O.topk(scores.astype(np.float32), 7)
+    got = D._topk(dev(scores.astype(np.float32))[0], K=7)
+    for a, b in zip(want, got):
+        np.testing.assert_array_equal(b.cpu().numpy(), a)
