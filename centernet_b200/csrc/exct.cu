@@ -301,6 +301,7 @@ int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_hea
   for (int q = 0; q < 4; ++q) {
     SelectPlan pq = pl;
     pq.use_tma = pq.use_tma && ((reinterpret_cast<uintptr_t>(maps[q]) & 15u) == 0);
+    if (!pq.use_tma) { pq.hot = 0; pq.seg_cap = pq.K; }
     FinalizeOut o = {lists[q]->scores, lists[q]->inds, lists[q]->clses, lists[q]->ys, lists[q]->xs,
                      nullptr, nullptr, 0, nullptr};
     rc = run_select(maps[q], pq, o, sel_ws, stream);

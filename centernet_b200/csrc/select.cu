@@ -194,14 +194,14 @@ __device__ void finalize_image(const float *__restrict__ src, const SelectPlan &
   int total = 0;
   for (int slot = 0; slot <= i1 - i0; ++slot) {
     const int n = __ldcg(cand_cnt + (size_t)b * pl.max_slots + slot);
-    const u64 *seg = cand + ((size_t)b * pl.max_slots + slot) * K;
+    const u64 *seg = cand + ((size_t)b * pl.max_slots + slot) * pl.seg_cap;
     for (int t = tid; t < n; t += G::n()) sbuf[total + t] = __ldcg(seg + t);
     total += n;
   }
   const int n = next_pow2(max(total, K));
   for (int t = total + tid; t < n; t += G::n()) sbuf[t] = 0ull;
   G::sync();
-  if (i1 > i0) group_sort_desc<G>(sbuf, n);  // a single segment arrives sorted already
+  group_sort_desc<G>(sbuf, n);  // segments may be unsorted supersets (hot kernel)
   if (total < K) {
     const long long N = (long long)pl.C * pl.H * pl.W;
     finalize_fill<NMS, G>(src + (long long)b * N, pl, sbuf, total, K, s_tmp, s_red);
@@ -398,7 +398,7 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
     }
     const int i0 = cta_of_plane((long long)img * pl.C, pl.P, pl.n_cta);
     const int slot = (int)blockIdx.x - i0;
-    u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * K;
+    u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * pl.seg_cap;
     for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = outp[t];
     if (tid == 0) cand_cnt[(size_t)img * pl.max_slots + slot] = n_out;
     if (pl.fused_finalize) {
@@ -664,7 +664,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   uint64_t *full = reinterpret_cast<uint64_t *>(unused_masks + SEL_MASK_WORDS);
   int *s_cnt = reinterpret_cast<int *>(full + SEL_STAGES);   // [0] count [1] overflow [2] last flag [3] compaction
   uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_cnt + 4);
-  __shared__ __align__(8) uint64_t sdone[SEL_STAGES];        // 32 warp arrivals: stage consumed
+  __shared__ int s_arr[SEL_STAGES];                          // warps done with the stage (last one re-arms it)
   __shared__ int s_flag[4];                                  // compaction rendezvous requested for unit (u & 3)
   __shared__ int s_tmp[32];
   __shared__ u64 s_red[32];
@@ -698,7 +698,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     s_flag[0] = s_flag[1] = s_flag[2] = s_flag[3] = 0;
     for (int s = 0; s < SEL_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&sdone[s], SEL_WARPS);
+      s_arr[s] = 0;
     }
     mbar_fence_init();
   }
@@ -718,6 +718,33 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     const int slot = atomicAdd(&s_cnt[0], 1);
     if (slot < SEL_CAP) buf[slot] = make_key(bits, flat);
     else s_cnt[1] = 1;
+  };
+
+  // ---- CTA-wide compaction of the key buffer against the current threshold (rendezvous, rare)
+  auto compact = [&](int slot_idx) {
+    __syncthreads();
+    if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+    __syncthreads();
+    const uint32_t tb = *s_thr;
+    const int cnt = min(s_cnt[0], SEL_CAP);
+    u64 mine[SEL_CAP / SEL_THREADS];
+#pragma unroll
+    for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j) {
+      const int t = tid + j * SEL_THREADS;
+      mine[j] = (t < cnt) ? buf[t] : 0ull;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (s_cnt[0] <= SEL_CAP) s_cnt[0] = 0;   // an overflowed buffer stays flagged; flush rescans
+      if (slot_idx >= 0) s_flag[slot_idx] = 0;
+    }
+    __syncthreads();
+    if (s_cnt[0] == 0) {
+#pragma unroll
+      for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j)
+        if (mine[j] != 0ull && key_bits(mine[j]) >= tb) buf[atomicAdd(&s_cnt[0], 1)] = mine[j];
+    }
+    __syncthreads();
   };
 
   // ---- CTA-wide flush of image `img` (all threads; called at image boundaries only)
@@ -750,32 +777,17 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       cta_prune(buf, s_cnt, K);
       n_out = min(s_cnt[0], K);
     } else {
+      if (s_cnt[0] > pl.seg_cap) compact(-1);     // drop everything below the histogram threshold (>= K survive)
       const int cnt = s_cnt[0];
-      n_out = min(cnt, K);
-      if (cnt > K && cnt <= SEL_CAP / 2) {
-        if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
-        __syncthreads();
-        const uint32_t tb = *s_thr;
-        u64 *hi = buf + SEL_CAP / 2;
-        for (int t = tid; t < cnt; t += SEL_THREADS) {
-          const u64 key = buf[t];
-          if (key_bits(key) >= tb) hi[atomicAdd(&s_cnt[3], 1)] = key;
-        }
-        __syncthreads();
-        const int m = s_cnt[3];
-        const int n = next_pow2(m);
-        for (int t = m + tid; t < n; t += SEL_THREADS) hi[t] = 0ull;
-        __syncthreads();
-        cta_sort_desc(hi, n);
-        outp = hi;
-        n_out = min(m, K);
-      } else {
+      n_out = cnt;                                  // deliver unsorted: finalize sorts anyway
+      if (cnt > pl.seg_cap) {                       // still too many (ties in the threshold bin): exact cut
         cta_prune(buf, s_cnt, K);
+        n_out = min(cnt, K);
       }
     }
     const int i0 = cta_of_plane((long long)img * C, pl.P, pl.n_cta);
     const int slot = (int)blockIdx.x - i0;
-    u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * K;
+    u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * pl.seg_cap;
     for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = outp[t];
     if (tid == 0) cand_cnt[(size_t)img * pl.max_slots + slot] = n_out;
     __threadfence();
@@ -795,7 +807,10 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   };
 
   // ---- phase A + push of rows [y0, y0 + 4) of the plane in stage `st`
-  const bool first = (lane == 0), lastl = (lane == 31);
+  // Per row: 4 vertical FMNMX3, 2 SHFL, 2 FADD (lane-edge -inf, keeps the ALU pipe free), the
+  // horizontal max with the running threshold folded in, 4 compares and one (rarely taken) branch.
+  const bool first = (lane == 0);
+  const float edge_l = (lane == 0) ? NI : 0.0f, edge_r = (lane == 31) ? NI : 0.0f;
   auto sweep = [&](const float *st, int c, bool use_thr) {
     const int y0 = warp * 4;
     const float *p = st + (size_t)y0 * 128 + lane * 4;
@@ -808,15 +823,14 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     const uint32_t fbase = (uint32_t)c * (uint32_t)HW + (uint32_t)(y0 * 128 + lane * 4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      // the running threshold is re-read per row (one broadcast LDS): fresher = fewer pushes
-      const float thr_f = __uint_as_float(max(use_thr ? *(volatile uint32_t *)s_thr : 0u, 1u));
+      // threshold >= smallest positive float, so `b == max(.., thr)` also rejects b <= 0; it is
+      // re-read per row (one broadcast LDS): fresher threshold = fewer pushes
+      const float thr_f = __uint_as_float(use_thr ? max(*(volatile uint32_t *)s_thr, 1u) : 1u);
       const float4 a = r_[i], b = r_[i + 1], cc = r_[i + 2];
       const float v0 = fmax3(a.x, b.x, cc.x), v1 = fmax3(a.y, b.y, cc.y);
       const float v2 = fmax3(a.z, b.z, cc.z), v3 = fmax3(a.w, b.w, cc.w);
-      float l = __shfl_up_sync(0xffffffffu, v3, 1);
-      float r = __shfl_down_sync(0xffffffffu, v0, 1);
-      l = first ? NI : l;
-      r = lastl ? NI : r;
+      const float l = __shfl_up_sync(0xffffffffu, v3, 1) + edge_l;
+      const float r = __shfl_down_sync(0xffffffffu, v0, 1) + edge_r;
       const float m01 = fmaxf(v0, v1), m23 = fmaxf(v2, v3);
       const bool q0 = (b.x == fmax3(l, m01, thr_f));
       const bool q1 = (b.y == fmax3(m01, v2, thr_f));
@@ -832,33 +846,6 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     }
   };
 
-  // ---- CTA-wide compaction of the key buffer against the current threshold (rendezvous, rare)
-  auto compact = [&](int slot_idx) {
-    __syncthreads();
-    if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
-    __syncthreads();
-    const uint32_t tb = *s_thr;
-    const int cnt = min(s_cnt[0], SEL_CAP);
-    u64 mine[SEL_CAP / SEL_THREADS];
-#pragma unroll
-    for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j) {
-      const int t = tid + j * SEL_THREADS;
-      mine[j] = (t < cnt) ? buf[t] : 0ull;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      if (s_cnt[0] <= SEL_CAP) s_cnt[0] = 0;   // an overflowed buffer stays flagged; flush rescans
-      s_flag[slot_idx] = 0;
-    }
-    __syncthreads();
-    if (s_cnt[0] == 0) {
-#pragma unroll
-      for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j)
-        if (mine[j] != 0ull && key_bits(mine[j]) >= tb) buf[atomicAdd(&s_cnt[0], 1)] = mine[j];
-    }
-    __syncthreads();
-  };
-
   int img = (int)(p_begin / C), c = (int)(p_begin - (long long)img * C);
   int stage = 0, par = 0;
   bool fresh = true;  // first unit of an image in this CTA (CTA-uniform)
@@ -867,8 +854,9 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     mbar_wait(&full[stage], (uint32_t)par);
     if (*(volatile int *)&s_flag[u & 3]) compact(u & 3);   // set 3 units ago, before this plane's TMA was issued
     if (fresh) {
-      // bootstrap in three steps (rows 0-15, 16-47, 48-127), refreshing the threshold in between,
-      // so only ~600 of a dense plane's ~1800 peaks are ever pushed
+      // bootstrap in three steps (rows 0-15, 16-47, 48-127) with a threshold refresh after each,
+      // so only ~600 of a dense plane's ~1800 peaks are pushed and unit 1 already sees the
+      // threshold of a whole plane
       if (warp < 4) sweep(st, c, false);
       __syncthreads();
       if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
@@ -885,16 +873,19 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     } else {
       sweep(st, c, true);
     }
+    if (warp == (u & (SEL_WARPS - 1))) update_threshold(fine, coarse, lane, K, s_thr);  // partial counts are valid too
     __syncwarp();
-    if (first) mbar_arrive(&sdone[stage]);
-    if (warp == (u & (SEL_WARPS - 1))) {
-      update_threshold(fine, coarse, lane, K, s_thr);       // partial histograms give valid bounds too
-      mbar_wait(&sdone[stage], (uint32_t)par);                // all 32 warps are done with this stage
-      if (first && u + SEL_STAGES < total_units) {
-        // buffer half full: ask every warp to rendezvous at unit u+3 (nobody can start it before
-        // the TMA below is issued, so all of them will see the flag)
-        if (*(volatile int *)&s_cnt[0] > SEL_CAP / 2) s_flag[(u + SEL_STAGES) & 3] = 1;
-        issue(u + SEL_STAGES);
+    if (first) {
+      // last warp to finish this stage re-arms it (no waiting): TMA load of unit u+3
+      __threadfence_block();
+      if (atomicAdd(&s_arr[stage], 1) == SEL_WARPS - 1) {
+        s_arr[stage] = 0;
+        if (u + SEL_STAGES < total_units) {
+          // buffer half full: ask every warp to rendezvous at unit u+3 (nobody can start it before
+          // the TMA below is issued, so all of them will see the flag)
+          if (*(volatile int *)&s_cnt[0] > SEL_CAP / 2) s_flag[(u + SEL_STAGES) & 3] = 1;
+          issue(u + SEL_STAGES);
+        }
       }
     }
     // next unit
@@ -967,11 +958,17 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   }
   pl->n_cta = n_cta;
   pl->fused_finalize = ((long long)pl->max_slots * K <= SEL_CAP) ? 1 : 0;
+  pl->seg_cap = K;
+  pl->hot = 0;
+  if (nms && pl->use_tma && W == 128 && H == 128 && pl->rb == 128 && pl->fused_finalize && K <= 256) {
+    pl->hot = 1;
+    if (K <= 128 && (long long)pl->max_slots * 256 <= SEL_CAP) pl->seg_cap = 256;
+  }
   return CNB_OK;
 }
 
 size_t select_workspace_bytes(const SelectPlan &pl) {
-  const size_t keys = align_up((size_t)pl.n_img * pl.max_slots * pl.K * 8, 256);
+  const size_t keys = align_up((size_t)pl.n_img * pl.max_slots * (pl.seg_cap > 256 ? pl.seg_cap : 256) * 8, 256);
   const size_t cnts = align_up((size_t)pl.n_img * pl.max_slots * 4, 256);
   const size_t done = align_up((size_t)pl.n_img * 4, 256);
   return keys + cnts + done;
@@ -1000,7 +997,7 @@ static int launch_select(const float *src, const SelectPlan &pl, const FinalizeO
                          int *done, cudaStream_t stream) {
   if (pl.fused_finalize) CNB_CUDA(cudaMemsetAsync(done, 0, (size_t)pl.n_img * 4, stream));
   int rc;
-  if (NMS && pl.use_tma && pl.W == 128 && pl.H == 128 && pl.rb == 128 && pl.fused_finalize && pl.K <= 256) {
+  if (NMS && pl.hot) {
     const size_t smem1 = stage1_smem_bytes();
     static thread_local int hot_dev = -1;
     int dev = 0;
@@ -1023,7 +1020,7 @@ static int launch_select(const float *src, const SelectPlan &pl, const FinalizeO
     rc = launch_stage1<NMS, false, 0>(src, pl, out, cand, cnt, done, stream);
   if (rc != CNB_OK) return rc;
   if (!pl.fused_finalize) {
-    const size_t smem2 = (size_t)next_pow2(pl.max_slots * pl.K > pl.K ? pl.max_slots * pl.K : pl.K) * 8;
+    const size_t smem2 = (size_t)next_pow2(pl.max_slots * pl.seg_cap > pl.K ? pl.max_slots * pl.seg_cap : pl.K) * 8;
     CNB_CUDA(cudaFuncSetAttribute(k_select_finalize<NMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     k_select_finalize<NMS><<<pl.n_img, 1024, smem2, stream>>>(src, pl, cand, cnt, out);
     CNB_CHECK_LAUNCH("select finalize");
@@ -1035,7 +1032,7 @@ static int launch_select(const float *src, const SelectPlan &pl, const FinalizeO
 int run_select(const float *src, const SelectPlan &pl, const FinalizeOut &out, void *ws, cudaStream_t stream) {
   char *p = reinterpret_cast<char *>(ws);
   u64 *cand = reinterpret_cast<u64 *>(p);
-  p += align_up((size_t)pl.n_img * pl.max_slots * pl.K * 8, 256);
+  p += align_up((size_t)pl.n_img * pl.max_slots * (pl.seg_cap > 256 ? pl.seg_cap : 256) * 8, 256);
   int *cnt = reinterpret_cast<int *>(p);
   p += align_up((size_t)pl.n_img * pl.max_slots * 4, 256);
   int *done = reinterpret_cast<int *>(p);

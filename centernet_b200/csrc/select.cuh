@@ -29,6 +29,8 @@ struct SelectPlan {
   int nms;
   int clamp_one;  // order by min(score, 1): exct_decode clamps the NMS'd maps before _topk (decode.py:299-302)
   int fused_finalize;  // last CTA of an image merges its segments inside stage 1
+  int seg_cap;    // keys per candidate segment (>= K; the hot kernel delivers unsorted supersets)
+  int hot;        // 128x128 planes, TMA, NMS, fused finalize, K <= 256: warp-asynchronous kernel
   long long P;    // planes = n_img * C
 };
 
