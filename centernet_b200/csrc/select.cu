@@ -31,12 +31,38 @@ namespace cnb {
 
 typedef unsigned long long u64;
 
-__host__ __device__ __forceinline__ long long cta_first_plane(long long cta, long long P, int n_cta) {
-  return cta * P / n_cta;
+// Contiguous partition of the B*C planes over n_cta CTAs.  Planes cost 1, every image boundary costs
+// `wb` extra planes (the CTA that crosses it pays a flush, a bootstrap and usually the finalize), so
+// ranges that contain a boundary get correspondingly fewer planes.  wb = 0 is the plain equal split.
+struct Part {
+  long long P;
+  int n_cta, C, wb;
+};
+__host__ __device__ __forceinline__ long long cta_first_plane(long long cta, const Part &q) {
+  const long long blk = (long long)q.C + q.wb;
+  const long long ftot = (q.P / q.C) * blk;
+  const long long T = cta * ftot / q.n_cta;
+  const long long m = T / blk, rem = T - m * blk;
+  return m * q.C + (rem < q.C ? rem : q.C);
 }
-// CTA whose range contains plane p: largest i with floor(i*P/n) <= p.
-__host__ __device__ __forceinline__ int cta_of_plane(long long p, long long P, int n_cta) {
-  return (int)(((p + 1) * (long long)n_cta - 1) / P);
+// CTA whose range contains plane p: largest i with cta_first_plane(i) <= p.
+__host__ __device__ __forceinline__ int cta_of_plane(long long p, const Part &q) {
+  int lo = 0, hi = q.n_cta - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (cta_first_plane(mid, q) <= p) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+// Device side: the host-computed table (no 64-bit divisions on the GPU).
+__device__ __forceinline__ long long plan_first_plane(const SelectPlan &pl, int cta) { return pl.cta_start[cta]; }
+__device__ __forceinline__ int plan_cta_of_plane(const SelectPlan &pl, long long p) {
+  int lo = 0, hi = pl.n_cta - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)pl.cta_start[mid] <= p) lo = mid; else hi = mid - 1;
+  }
+  return lo;
 }
 
 // ------------------------------------------------------------------ cooperating-thread groups
@@ -73,7 +99,44 @@ __device__ __forceinline__ void group_sort_desc(u64 *buf, int n) {
     }
   }
 }
-__device__ __forceinline__ void cta_sort_desc(u64 *buf, int n) { group_sort_desc<CtaGroup>(buf, n); }
+// CTA-wide bitonic sort for n <= blockDim.x: one key per thread in a register; compare-exchange
+// partners closer than a warp come by shuffle (no barrier), only the strides >= 32 go through
+// shared memory (15 of the 55 stages at n = 1024).
+__device__ __forceinline__ void cta_sort_desc_reg(u64 *buf, int n) {
+  const int i = threadIdx.x;
+  const bool part = (i >> 5) < ((n + 31) >> 5);   // warps that hold keys; the others only keep the barriers company
+  u64 v = (i < n) ? buf[i] : 0ull;
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      u64 p = 0ull;
+      if (j >= 32) {
+        __syncthreads();
+        if (i < n) buf[i] = v;
+        __syncthreads();
+        if (i < n) p = buf[i ^ j];
+      } else if (part) {
+        const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, j);
+        const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), j);
+        p = ((u64)hi << 32) | lo;
+      }
+      if (part) {
+        const bool take_max = (((i & k) == 0) == ((i & j) == 0));
+        v = take_max ? (v > p ? v : p) : (v < p ? v : p);
+      }
+    }
+  }
+  __syncthreads();
+  if (i < n) buf[i] = v;
+  __syncthreads();
+}
+__device__ __forceinline__ void cta_sort_desc(u64 *buf, int n) {
+  if (n <= (int)blockDim.x && blockDim.x >= 64) cta_sort_desc_reg(buf, n);
+  else group_sort_desc<CtaGroup>(buf, n);
+}
+template <typename G>
+__device__ __forceinline__ void sort_desc_best(u64 *buf, int n) { group_sort_desc<G>(buf, n); }
+template <>
+__device__ __forceinline__ void sort_desc_best<CtaGroup>(u64 *buf, int n) { cta_sort_desc(buf, n); }
 
 __host__ __device__ __forceinline__ int next_pow2(int v) {
   int n = 2;
@@ -90,7 +153,7 @@ __device__ __forceinline__ u64 group_prune(u64 *buf, int *s_cnt, int K) {
   const int n = next_pow2(cnt);
   for (int t = cnt + G::tid(); t < n; t += G::n()) buf[t] = 0ull;
   G::sync();
-  group_sort_desc<G>(buf, n);
+  sort_desc_best<G>(buf, n);
   u64 thr = 0ull;
   if (cnt >= K) thr = buf[K - 1];
   G::sync();
@@ -99,6 +162,51 @@ __device__ __forceinline__ u64 group_prune(u64 *buf, int *s_cnt, int K) {
   return thr;
 }
 __device__ __forceinline__ u64 cta_prune(u64 *buf, int *s_cnt, int K) { return group_prune<CtaGroup>(buf, s_cnt, K); }
+
+// ---- running threshold: 2-level histogram of the pushed scores (128 bins per octave over
+// [2^-16, 1), 32 coarse x 64 fine).  The lower edge of the highest bin whose suffix count reaches
+// K is a valid lower bound of the image's K-th best score: at least K real candidates lie above it.
+__device__ __forceinline__ int hist_bin(uint32_t bits) {
+  const int e = (int)(bits >> 16) - ((127 - 16) << 7);
+  return min(max(e, 0), SEL_HIST_FINE - 1);
+}
+__device__ __forceinline__ uint32_t bin_lower_bits(int b) {
+  return b <= 0 ? 1u : ((uint32_t)(b + ((127 - 16) << 7)) << 16);
+}
+// Highest of 64 bins whose suffix count is >= need (or -1); *rem = need - (count strictly above it).
+__device__ __forceinline__ int warp_suffix_pick(const int *bins, int lane, int need, int *rem) {
+  const int c0 = bins[2 * lane], c1 = bins[2 * lane + 1];
+  const int s = c0 + c1;
+  int suf = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += t;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, suf >= need);
+  if (!bal) return -1;
+  const int L = 31 - __clz(bal);
+  const int above = __shfl_sync(0xffffffffu, suf - s, L);
+  const int c1L = __shfl_sync(0xffffffffu, c1, L);
+  if (above + c1L >= need) {
+    *rem = need - above;
+    return 2 * L + 1;
+  }
+  *rem = need - above - c1L;
+  return 2 * L;
+}
+// warp 0 only
+__device__ __forceinline__ void update_threshold(const int *fine, const int *coarse, int lane, int K,
+                                                 uint32_t *s_thr) {
+  int rem = 0, rem2 = 0;
+  const int cb = warp_suffix_pick(coarse, lane, K, &rem);
+  uint32_t bits = 0u;
+  if (cb >= 0) {
+    const int fb = warp_suffix_pick(fine + cb * 64, lane, rem, &rem2);
+    bits = bin_lower_bits(cb * 64 + max(fb, 0));
+  }
+  if (lane == 0) *s_thr = bits;
+}
 
 // ------------------------------------------------------------------ finalize (shared by both paths)
 // v'(i): the reference's heat*keep value of flat pixel i (keep only in NMS mode).
@@ -184,24 +292,64 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
 
 // Merge the segments of image b (written by the stage-1 CTAs i0..i1), sort, emit.
 // sbuf must hold next_pow2(max(max_slots*K, K)) keys.  All threads of the CTA call.
+__device__ long long g_fin_t[4];
 template <bool NMS, typename G>
 __device__ void finalize_image(const float *__restrict__ src, const SelectPlan &pl, int b,
                                const u64 *__restrict__ cand, const int *__restrict__ cand_cnt,
-                               const FinalizeOut &out, u64 *sbuf, int *s_tmp, u64 *s_red) {
+                               const FinalizeOut &out, u64 *sbuf, int *s_tmp, u64 *s_red,
+                               const uint32_t *cand_thr = nullptr) {
   const int tid = G::tid(), K = pl.K;
-  const int i0 = cta_of_plane((long long)b * pl.C, pl.P, pl.n_cta);
-  const int i1 = cta_of_plane((long long)(b + 1) * pl.C - 1, pl.P, pl.n_cta);
+  if (tid == 0) {  // the binary search costs ~1k instructions: one thread does it
+    s_tmp[30] = plan_cta_of_plane(pl, (long long)b * pl.C);
+    s_tmp[31] = plan_cta_of_plane(pl, (long long)(b + 1) * pl.C - 1);
+  }
+  G::sync();
+  const int i0 = s_tmp[30], i1 = s_tmp[31];
   int total = 0;
+  long long tq0 = clock64();
   for (int slot = 0; slot <= i1 - i0; ++slot) {
     const int n = __ldcg(cand_cnt + (size_t)b * pl.max_slots + slot);
     const u64 *seg = cand + ((size_t)b * pl.max_slots + slot) * pl.seg_cap;
     for (int t = tid; t < n; t += G::n()) sbuf[total + t] = __ldcg(seg + t);
     total += n;
   }
-  const int n = next_pow2(max(total, K));
-  for (int t = total + tid; t < n; t += G::n()) sbuf[t] = 0ull;
   G::sync();
-  group_sort_desc<G>(sbuf, n);  // segments may be unsorted supersets (hot kernel)
+  long long tq1 = clock64();
+  if (cand_thr != nullptr && total > 2 * K && total <= 2 * G::n()) {
+    // every segment comes with a valid lower bound of the image's K-th best score (the K-th best of
+    // a subset never exceeds the K-th best of the whole), so the largest of them is one too: drop
+    // everything below it before sorting (>= K survive, usually ~1.2 K; <= 2 keys per thread here)
+    uint32_t tb = 0u;
+    for (int slot = 0; slot <= i1 - i0; ++slot) tb = max(tb, __ldcg(cand_thr + (size_t)b * pl.max_slots + slot));
+    if (tid == 0) s_tmp[0] = 0;
+    const u64 mine0 = (tid < total) ? sbuf[tid] : 0ull;
+    const u64 mine1 = (tid + G::n() < total) ? sbuf[tid + G::n()] : 0ull;
+    G::sync();
+    if (mine0 != 0ull && key_bits(mine0) >= tb) sbuf[atomicAdd(&s_tmp[0], 1)] = mine0;
+    if (mine1 != 0ull && key_bits(mine1) >= tb) sbuf[atomicAdd(&s_tmp[0], 1)] = mine1;
+    G::sync();
+    total = s_tmp[0];
+    G::sync();
+  }
+  if (total <= 256 && total <= G::n() && G::n() >= 256) {
+    // few survivors: rank sort (every key counts the keys above it; no dependent network stages)
+    const u64 mine = (tid < total) ? sbuf[tid] : 0ull;
+    int rank = 0;
+    if (tid < total)
+      for (int t = 0; t < total; ++t) rank += (sbuf[t] > mine) ? 1 : 0;
+    G::sync();
+    const int n2 = max(total, K);
+    for (int t = total + tid; t < n2; t += G::n()) sbuf[t] = 0ull;
+    if (tid < total) sbuf[rank] = mine;
+    G::sync();
+  } else {
+    const int n = next_pow2(max(total, K));
+    for (int t = total + tid; t < n; t += G::n()) sbuf[t] = 0ull;
+    G::sync();
+    sort_desc_best<G>(sbuf, n);  // segments may be unsorted supersets (hot kernel)
+  }
+  const int n = next_pow2(max(total, K));
+  long long tq2 = clock64();
   if (total < K) {
     const long long N = (long long)pl.C * pl.H * pl.W;
     finalize_fill<NMS, G>(src + (long long)b * N, pl, sbuf, total, K, s_tmp, s_red);
@@ -243,6 +391,12 @@ __device__ void finalize_image(const float *__restrict__ src, const SelectPlan &
     }
   }
   G::sync();
+  if (pl.dbg && tid == 0 && b == 5) {
+    pl.dbg[148 * 8 + 0] = (unsigned long long)(tq1 - tq0);
+    pl.dbg[148 * 8 + 1] = (unsigned long long)(tq2 - tq1);
+    pl.dbg[148 * 8 + 2] = (unsigned long long)(clock64() - tq2);
+    pl.dbg[148 * 8 + 3] = (unsigned long long)n;
+  }
 }
 
 // ------------------------------------------------------------------ stage 1
@@ -264,51 +418,6 @@ __device__ __forceinline__ UnitGeom unit_geom(const SelectPlan &pl, long long p_
   g.ra = max(g.r0 - 1, 0);
   g.rb = min(g.r1 + 1, pl.H);
   return g;
-}
-
-// ---- running threshold: 2-level histogram of the pushed scores (128 bins per octave over
-// [2^-16, 1), 32 coarse x 64 fine).  The lower edge of the highest bin whose suffix count reaches
-// K is a valid lower bound of the image's K-th best score: at least K real candidates lie above it.
-__device__ __forceinline__ int hist_bin(uint32_t bits) {
-  const int e = (int)(bits >> 16) - ((127 - 16) << 7);
-  return min(max(e, 0), SEL_HIST_FINE - 1);
-}
-__device__ __forceinline__ uint32_t bin_lower_bits(int b) {
-  return b <= 0 ? 1u : ((uint32_t)(b + ((127 - 16) << 7)) << 16);
-}
-// Highest of 64 bins whose suffix count is >= need (or -1); *rem = need - (count strictly above it).
-__device__ __forceinline__ int warp_suffix_pick(const int *bins, int lane, int need, int *rem) {
-  const int c0 = bins[2 * lane], c1 = bins[2 * lane + 1];
-  const int s = c0 + c1;
-  int suf = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_down_sync(0xffffffffu, suf, o);
-    if (lane + o < 32) suf += t;
-  }
-  const uint32_t bal = __ballot_sync(0xffffffffu, suf >= need);
-  if (!bal) return -1;
-  const int L = 31 - __clz(bal);
-  const int above = __shfl_sync(0xffffffffu, suf - s, L);
-  const int c1L = __shfl_sync(0xffffffffu, c1, L);
-  if (above + c1L >= need) {
-    *rem = need - above;
-    return 2 * L + 1;
-  }
-  *rem = need - above - c1L;
-  return 2 * L;
-}
-// warp 0 only
-__device__ __forceinline__ void update_threshold(const int *fine, const int *coarse, int lane, int K,
-                                                 uint32_t *s_thr) {
-  int rem = 0, rem2 = 0;
-  const int cb = warp_suffix_pick(coarse, lane, K, &rem);
-  uint32_t bits = 0u;
-  if (cb >= 0) {
-    const int fb = warp_suffix_pick(fine + cb * 64, lane, rem, &rem2);
-    bits = bin_lower_bits(cb * 64 + max(fb, 0));
-  }
-  if (lane == 0) *s_thr = bits;
 }
 
 // MODE 0: generic geometry; 1: one 128-column block per row (W <= 128, W % 4 == 0, TMA);
@@ -334,8 +443,8 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = pl.H, W = pl.W, Wp = pl.Wp, ncb = pl.ncb, K = pl.K;
   const long long HW = (long long)H * W;
-  const long long p_begin = cta_first_plane(blockIdx.x, pl.P, pl.n_cta);
-  const long long p_end = cta_first_plane(blockIdx.x + 1, pl.P, pl.n_cta);
+  const long long p_begin = plan_first_plane(pl, blockIdx.x);
+  const long long p_end = plan_first_plane(pl, blockIdx.x + 1);
   const int total_units = (int)(p_end - p_begin) * pl.upp;
   const float NI = CNB_NEG_INF;
 
@@ -396,7 +505,9 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
     } else {
       cta_prune(buf, s_cnt, K);
     }
-    const int i0 = cta_of_plane((long long)img * pl.C, pl.P, pl.n_cta);
+    if (tid == 0) s_tmp[28] = plan_cta_of_plane(pl, (long long)img * pl.C);
+    __syncthreads();
+    const int i0 = s_tmp[28];
     const int slot = (int)blockIdx.x - i0;
     u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * pl.seg_cap;
     for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = outp[t];
@@ -405,7 +516,7 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
       __threadfence();
       __syncthreads();
       if (tid == 0) {
-        const int i1 = cta_of_plane((long long)(img + 1) * pl.C - 1, pl.P, pl.n_cta);
+        const int i1 = plan_cta_of_plane(pl, (long long)(img + 1) * pl.C - 1);
         const int ticket = atomicAdd(&img_done[img], 1);
         s_cnt[2] = (ticket == i1 - i0) ? 1 : 0;
       }
@@ -654,7 +765,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict__ cand, int *__restrict__ cand_cnt,
-             int *__restrict__ img_done, const FinalizeOut fout) {
+             int *__restrict__ img_done, uint32_t *__restrict__ cand_thr, const FinalizeOut fout) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *stages = reinterpret_cast<float *>(smem_raw);
   u64 *buf = reinterpret_cast<u64 *>(smem_raw + (size_t)SEL_STAGES * SEL_STAGE_BYTES);
@@ -672,8 +783,8 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = pl.K, C = pl.C;
   constexpr int HW = 128 * 128;
-  const long long p_begin = cta_first_plane(blockIdx.x, pl.P, pl.n_cta);
-  const long long p_end = cta_first_plane(blockIdx.x + 1, pl.P, pl.n_cta);
+  const long long p_begin = plan_first_plane(pl, blockIdx.x);
+  const long long p_end = plan_first_plane(pl, blockIdx.x + 1);
   const int total_units = (int)(p_end - p_begin);
   const float NI = CNB_NEG_INF;
 
@@ -748,11 +859,17 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   };
 
   // ---- CTA-wide flush of image `img` (all threads; called at image boundaries only)
+  long long t_sync = 0, t_fin = 0, t_cut = 0;
+  int n_rescan = 0, n_fin = 0, n_prune = 0;
   auto flush = [&](int img) {
+    long long tf0 = clock64();
     __syncthreads();
+    t_sync += clock64() - tf0;
+    tf0 = clock64();
     const u64 *outp = buf;
     int n_out;
     if (s_cnt[1]) {
+      ++n_rescan;
       // the buffer overflowed at some point: rebuild this CTA's segment exactly from global memory
       __syncthreads();
       if (tid == 0) s_cnt[0] = 0;
@@ -778,28 +895,43 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       n_out = min(s_cnt[0], K);
     } else {
       if (s_cnt[0] > pl.seg_cap) compact(-1);     // drop everything below the histogram threshold (>= K survive)
+      else {
+        if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+        __syncthreads();
+      }
       const int cnt = s_cnt[0];
       n_out = cnt;                                  // deliver unsorted: finalize sorts anyway
       if (cnt > pl.seg_cap) {                       // still too many (ties in the threshold bin): exact cut
         cta_prune(buf, s_cnt, K);
         n_out = min(cnt, K);
+        ++n_prune;
       }
     }
-    const int i0 = cta_of_plane((long long)img * C, pl.P, pl.n_cta);
+    t_cut += clock64() - tf0;
+    if (tid == 0) {
+      s_tmp[28] = plan_cta_of_plane(pl, (long long)img * C);
+      s_tmp[29] = plan_cta_of_plane(pl, (long long)(img + 1) * C - 1);
+    }
+    __syncthreads();
+    const int i0 = s_tmp[28];
     const int slot = (int)blockIdx.x - i0;
     u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * pl.seg_cap;
     for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = outp[t];
-    if (tid == 0) cand_cnt[(size_t)img * pl.max_slots + slot] = n_out;
+    if (tid == 0) {
+      cand_cnt[(size_t)img * pl.max_slots + slot] = n_out;
+      // histogram threshold = valid lower bound of the image's K-th best (0 after an exact rebuild)
+      cand_thr[(size_t)img * pl.max_slots + slot] = s_cnt[1] ? 0u : *s_thr;
+    }
     __threadfence();
     __syncthreads();
-    if (tid == 0) {
-      const int i1 = cta_of_plane((long long)(img + 1) * C - 1, pl.P, pl.n_cta);
-      s_cnt[2] = (atomicAdd(&img_done[img], 1) == i1 - i0) ? 1 : 0;
-    }
+    if (tid == 0) s_cnt[2] = (atomicAdd(&img_done[img], 1) == s_tmp[29] - i0) ? 1 : 0;
     __syncthreads();
     if (s_cnt[2]) {  // every segment of this image is in global memory: merge + emit here
+      const long long tq = clock64();
       __threadfence();
-      finalize_image<true, CtaGroup>(src, pl, img, cand, cand_cnt, fout, buf, s_tmp, s_red);
+      finalize_image<true, CtaGroup>(src, pl, img, cand, cand_cnt, fout, buf, s_tmp, s_red, cand_thr);
+      t_fin += clock64() - tq;
+      ++n_fin;
     }
     __syncthreads();
     reset_state();
@@ -811,7 +943,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   // horizontal max with the running threshold folded in, 4 compares and one (rarely taken) branch.
   const bool first = (lane == 0);
   const float edge_l = (lane == 0) ? NI : 0.0f, edge_r = (lane == 31) ? NI : 0.0f;
-  auto sweep = [&](const float *st, int c, bool use_thr) {
+  auto sweep = [&](const float *st, int c, bool use_thr, int i_lo, int i_hi) {
     const int y0 = warp * 4;
     const float *p = st + (size_t)y0 * 128 + lane * 4;
     const float4 ninf = make_float4(NI, NI, NI, NI);
@@ -823,6 +955,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     const uint32_t fbase = (uint32_t)c * (uint32_t)HW + (uint32_t)(y0 * 128 + lane * 4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+      if (i < i_lo || i >= i_hi) continue;   // warp-uniform (bootstrap sweeps a row subset)
       // threshold >= smallest positive float, so `b == max(.., thr)` also rejects b <= 0; it is
       // re-read per row (one broadcast LDS): fresher threshold = fewer pushes
       const float thr_f = __uint_as_float(use_thr ? max(*(volatile uint32_t *)s_thr, 1u) : 1u);
@@ -849,29 +982,32 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   int img = (int)(p_begin / C), c = (int)(p_begin - (long long)img * C);
   int stage = 0, par = 0;
   bool fresh = true;  // first unit of an image in this CTA (CTA-uniform)
+  const long long t_start = clock64();
+  long long t_wait = 0, t_boot = 0, t_flush = 0;
+  int n_flush = 0;
   for (int u = 0; u < total_units; ++u) {
     const float *st = stages + (size_t)stage * (SEL_STAGE_BYTES / 4);
+    long long t0 = clock64();
     mbar_wait(&full[stage], (uint32_t)par);
+    t_wait += clock64() - t0;
+    t0 = clock64();
     if (*(volatile int *)&s_flag[u & 3]) compact(u & 3);   // set 3 units ago, before this plane's TMA was issued
     if (fresh) {
-      // bootstrap in three steps (rows 0-15, 16-47, 48-127) with a threshold refresh after each,
-      // so only ~600 of a dense plane's ~1800 peaks are pushed and unit 1 already sees the
-      // threshold of a whole plane
-      if (warp < 4) sweep(st, c, false);
+      // bootstrap: every warp first sweeps only its first row (a 25% sample of the plane, all warps
+      // busy), a threshold is derived, then the remaining rows are swept against it and the
+      // threshold is refreshed once more, so unit 1 already sees the K-th best of a whole plane.
+      sweep(st, c, false, 0, 1);
       __syncthreads();
       if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
       __syncthreads();
-      if (warp >= 4 && warp < 12) sweep(st, c, true);
-      __syncthreads();
-      if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
-      __syncthreads();
-      if (warp >= 12) sweep(st, c, true);
+      sweep(st, c, true, 1, 4);
       __syncthreads();
       if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
       __syncthreads();
       fresh = false;
+      t_boot += clock64() - t0;
     } else {
-      sweep(st, c, true);
+      sweep(st, c, true, 0, 4);
     }
     if (warp == (u & (SEL_WARPS - 1))) update_threshold(fine, coarse, lane, K, s_thr);  // partial counts are valid too
     __syncwarp();
@@ -889,15 +1025,36 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       }
     }
     // next unit
+    t0 = clock64();
     if (++c == C) {
       flush(img);
       c = 0;
       ++img;
       fresh = true;
+      t_flush += clock64() - t0;
+      ++n_flush;
     } else if (u == total_units - 1) {
       flush(img);
+      t_flush += clock64() - t0;
+      ++n_flush;
     }
     if (++stage == SEL_STAGES) { stage = 0; par ^= 1; }
+  }
+  if (pl.dbg && tid == 0) {
+    unsigned long long *d = pl.dbg + (size_t)blockIdx.x * 8;
+    d[0] = (unsigned long long)(clock64() - t_start);
+    d[1] = (unsigned long long)t_wait;
+    d[2] = (unsigned long long)t_boot;
+    d[3] = (unsigned long long)t_flush;
+    d[4] = (unsigned long long)n_flush;
+    d[5] = (unsigned long long)total_units;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    d[6] = smid;
+    d[7] = (unsigned long long)n_fin | ((unsigned long long)n_rescan << 8) | ((unsigned long long)n_prune << 16);
+    d[6] = (unsigned long long)t_sync;
+    d[5] = (unsigned long long)t_cut;
+    d[4] = (unsigned long long)n_flush | ((unsigned long long)t_fin << 8);
   }
 }
 
@@ -919,6 +1076,9 @@ static size_t stage1_smem_bytes() {
          (size_t)(SEL_HIST_FINE + SEL_HIST_COARSE) * 4 + (size_t)SEL_MASK_WORDS * 4 + SEL_STAGES * 8 + 32;
 }
 
+static thread_local unsigned long long *t_dbg = nullptr;
+extern "C" void cnb_debug_set_select_stats(void *p) { t_dbg = reinterpret_cast<unsigned long long *>(p); }
+
 int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, int nms, SelectPlan *pl) {
   CNB_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0 && K > 0, CNB_EINVAL,
               "top-k: non-positive dimension (n_img=%d c=%d h=%d w=%d k=%d)", n_img, C, H, W, K);
@@ -928,6 +1088,7 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   CNB_REQUIRE((long long)C * H * W < (1ll << 32), CNB_EUNSUPPORTED, "top-k: c*h*w must be < 2^32");
   pl->n_img = n_img; pl->C = C; pl->H = H; pl->W = W; pl->K = K; pl->nms = nms;
   pl->clamp_one = 0;
+  pl->dbg = t_dbg;
   pl->Wp = (W + 3) / 4 * 4;
   pl->ncb = (W + 127) / 128;
   pl->P = (long long)n_img * C;
@@ -942,12 +1103,25 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   }
   pl->upp = (H + pl->rb - 1) / pl->rb;
   int n_cta = num_sms();
+  if (n_cta > SEL_MAX_CTA) n_cta = SEL_MAX_CTA;
   if ((long long)n_cta > pl->P) n_cta = (int)pl->P;
+  // image boundaries cost the crossing CTA ~7 planes' worth of cycles in the hot kernel
+  // (measured: flush + bootstrap + finalize); only worth modelling when ranges are long
+  int wb = 0;
+  if (nms && pl->use_tma && W == 128 && H == 128 && K <= 256 && C > 1 && pl->P / n_cta >= 16) wb = 7;
   for (;;) {
+    Part q;
+    q.P = pl->P; q.n_cta = n_cta; q.C = C; q.wb = wb;
+    bool ok = true;
+    for (int i = 0; i < n_cta && ok; ++i) ok = cta_first_plane(i + 1, q) > cta_first_plane(i, q);
+    if (!ok) {  // weighted split produced an empty range: fall back to the plain split
+      wb = 0;
+      continue;
+    }
     int ms = 1;
     for (int b = 0; b < n_img; ++b) {
-      const int i0 = cta_of_plane((long long)b * C, pl->P, n_cta);
-      const int i1 = cta_of_plane((long long)(b + 1) * C - 1, pl->P, n_cta);
+      const int i0 = cta_of_plane((long long)b * C, q);
+      const int i1 = cta_of_plane((long long)(b + 1) * C - 1, q);
       if (i1 - i0 + 1 > ms) ms = i1 - i0 + 1;
     }
     if ((long long)ms * K <= SEL_FIN_MAX || n_cta == 1) {
@@ -957,6 +1131,12 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
     n_cta = (n_cta * 3) / 4 > 0 ? (n_cta * 3) / 4 : 1;
   }
   pl->n_cta = n_cta;
+  pl->wb = wb;
+  {
+    Part q;
+    q.P = pl->P; q.n_cta = n_cta; q.C = C; q.wb = wb;
+    for (int i = 0; i <= n_cta; ++i) pl->cta_start[i] = (int)cta_first_plane(i, q);
+  }
   pl->fused_finalize = ((long long)pl->max_slots * K <= SEL_CAP) ? 1 : 0;
   pl->seg_cap = K;
   pl->hot = 0;
@@ -971,7 +1151,7 @@ size_t select_workspace_bytes(const SelectPlan &pl) {
   const size_t keys = align_up((size_t)pl.n_img * pl.max_slots * (pl.seg_cap > 256 ? pl.seg_cap : 256) * 8, 256);
   const size_t cnts = align_up((size_t)pl.n_img * pl.max_slots * 4, 256);
   const size_t done = align_up((size_t)pl.n_img * 4, 256);
-  return keys + cnts + done;
+  return keys + cnts + done + cnts;  // + per-segment thresholds
 }
 
 template <bool NMS, bool TMA, int MODE>
@@ -994,7 +1174,7 @@ static int launch_stage1(const float *src, const SelectPlan &pl, const FinalizeO
 
 template <bool NMS>
 static int launch_select(const float *src, const SelectPlan &pl, const FinalizeOut &out, u64 *cand, int *cnt,
-                         int *done, cudaStream_t stream) {
+                         int *done, uint32_t *thr, cudaStream_t stream) {
   if (pl.fused_finalize) CNB_CUDA(cudaMemsetAsync(done, 0, (size_t)pl.n_img * 4, stream));
   int rc;
   if (NMS && pl.hot) {
@@ -1006,7 +1186,7 @@ static int launch_select(const float *src, const SelectPlan &pl, const FinalizeO
       CNB_CUDA(cudaFuncSetAttribute(k_select_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       hot_dev = dev;
     }
-    k_select_hot<<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, out);
+    k_select_hot<<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, thr, out);
     CNB_CHECK_LAUNCH("select stage 1 (hot)");
     count_launch();
     rc = CNB_OK;
@@ -1036,8 +1216,10 @@ int run_select(const float *src, const SelectPlan &pl, const FinalizeOut &out, v
   int *cnt = reinterpret_cast<int *>(p);
   p += align_up((size_t)pl.n_img * pl.max_slots * 4, 256);
   int *done = reinterpret_cast<int *>(p);
-  return pl.nms ? launch_select<true>(src, pl, out, cand, cnt, done, stream)
-                : launch_select<false>(src, pl, out, cand, cnt, done, stream);
+  p += align_up((size_t)pl.n_img * 4, 256);
+  uint32_t *thr = reinterpret_cast<uint32_t *>(p);
+  return pl.nms ? launch_select<true>(src, pl, out, cand, cnt, done, thr, stream)
+                : launch_select<false>(src, pl, out, cand, cnt, done, thr, stream);
 }
 
 }  // namespace cnb

@@ -15,6 +15,7 @@ constexpr int SEL_HIST_COARSE = 64;      // 64 fine bins each (only the first FI
 constexpr int SEL_MASK_WORDS = 512;     // qualifying-pixel bitmask of one unit
 constexpr int SEL_RW = 4;               // rows per warp work item
 constexpr int SEL_MAX_K = 1024;
+constexpr int SEL_MAX_CTA = 192;        // stage-1 grid limit (one CTA per SM; B200 has 148)
 constexpr int SEL_FIN_MAX = 8192;       // separate-finalize sort capacity (keys); the fused finalize uses SEL_CAP
 
 struct SelectPlan {
@@ -31,7 +32,10 @@ struct SelectPlan {
   int fused_finalize;  // last CTA of an image merges its segments inside stage 1
   int seg_cap;    // keys per candidate segment (>= K; the hot kernel delivers unsorted supersets)
   int hot;        // 128x128 planes, TMA, NMS, fused finalize, K <= 256: warp-asynchronous kernel
+  int wb;         // partition weight of an image boundary, in planes (flush + bootstrap + finalize cost)
   long long P;    // planes = n_img * C
+  unsigned long long *dbg;  // optional per-CTA cycle counters (tuning only; null in normal use)
+  int cta_start[SEL_MAX_CTA + 1];  // first plane of every CTA's contiguous range (host-computed partition)
 };
 
 // Raw top-K outputs ([n_img, K] each, any pointer may be null) plus the fused ctdet epilogue.
