@@ -32,6 +32,7 @@ UNIT = "images/s"
 B_PER_GPU, C, H, W, K = 64, 80, 128, 128, 100
 ALG_BYTES_PER_IMAGE = C * H * W * 4 + K * 4 * 4 + K * 6 * 4   # 5,246,880 B
 N_ROT = 3                                                      # rotating input batches (3 x 352 MB >> 126 MB L2)
+NCU_TRAFFIC_BYTES = 338720512 + 4057088                        # measured DRAM read + write of one launch (profiles/)
 
 
 def synth(batch, device, seed):
@@ -250,8 +251,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        # the decode call is stage-1 (streams the heat map) + a small finalize kernel; the
-        # roofline is reported on the whole call, i.e. conservatively for the dominant kernel
+        # the decode call is ONE kernel launch in this geometry (k_select_hot: NMS + top-K + gathers +
+        # box assembly, finalize fused); per-launch time = CUDA-event time of the timed region / steps
         per_launch_s = ms_max * 1e-3 / args.steps
         achieved = ALG_BYTES_PER_IMAGE * B_PER_GPU / per_launch_s / 1e9
         out = {
@@ -265,8 +266,10 @@ def main():
                 "l2": "inputs > L2: %d rotating batches of %.0f MB" % (N_ROT, h2d / 1e6),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_select_stage1 + k_select_finalize (whole decode call)",
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                         "traffic_source": "profiles/r1_decode_hot_final_summary.csv (ncu --set full: "
+                                           "dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                         "kernel": "k_select_hot (the whole decode call is this one launch)",
                          "alg_bytes_per_launch": ALG_BYTES_PER_IMAGE * B_PER_GPU},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps},
