@@ -5,9 +5,8 @@
 // The fp32 additions are strictly sequential in the reference, so each row/column is
 // scanned by ONE thread in that order (a tree/warp scan would re-associate the sums and
 // break bit parity); parallelism comes from the B*C*H rows (or B*C*W columns).
-//   rows   : 64-row x 128-column tiles are staged through padded shared memory so global
-//            accesses stay coalesced while each thread walks its row; the reverse pass
-//            parks its result in `out`, the forward pass combines.
+//   rows   : one thread per row with 16-byte accesses (its 128-byte lines stay in L1 while it consumes
+//            them); the reverse pass parks its result in `out`, the forward pass combines.
 //   columns: thread-per-column is coalesced as is; `out` doubles as the scratch of the
 //            bottom-up pass (it stays in L2 between the two passes).
 #include "common.cuh"
@@ -24,74 +23,61 @@ __device__ __forceinline__ float combine(int mode, float w, float fwd, float rev
   return __fadd_rn(__fadd_rn(__fmul_rn(w, fwd), __fmul_rn(w, rev)), h);  // decode.py:72-73 order
 }
 
-__global__ void __launch_bounds__(AG_R) k_aggr_rows(const float *__restrict__ heat, float *__restrict__ out,
-                                                     long long nrows, int W, float w, int mode) {
-  extern __shared__ float ag_sm[];
-  float (*th)[AG_CW + 1] = reinterpret_cast<float (*)[AG_CW + 1]>(ag_sm);                         // heat tile
-  float (*tr)[AG_CW + 1] = reinterpret_cast<float (*)[AG_CW + 1]>(ag_sm + AG_R * (AG_CW + 1));  // reverse / result
-  const long long row0 = (long long)blockIdx.x * AG_R;
-  const int nr = (int)min((long long)AG_R, nrows - row0);
-  const int r = threadIdx.x;
-  const int nchunk = (W + AG_CW - 1) / AG_CW;
-  // ---- reverse pass (right aggregate, decode.py:30-41): chunks from the right edge inwards
-  float ret = 0.0f, hnext = 0.0f;
-  if (mode != 1) {
-    for (int ch = nchunk - 1; ch >= 0; --ch) {
-      const int c0 = ch * AG_CW, cw = min(AG_CW, W - c0);
-      for (int i = threadIdx.x; i < nr * cw; i += AG_R) {
-        const int rr = i / cw, cc = i - rr * cw;
-        th[rr][cc] = heat[(row0 + rr) * W + c0 + cc];
+// Rows: one thread walks one row with 16-byte accesses.  Neighbouring threads touch different 128-byte
+// lines, but every thread consumes each of its lines completely over 8 consecutive steps, so the lines
+// live in L1 for that long and DRAM still sees each byte once; 2048 threads per SM hide the latency.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_aggr_rows(const float *__restrict__ heat, float *__restrict__ out,
+                                                   long long nrows, int W, float w, int mode) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const float *hp = heat + row * W;
+  float *op = out + row * W;
+  float ret = 0.0f, hn = 0.0f;
+  if (mode != 1) {  // right aggregate (decode.py:30-41): from the right edge inwards, parked in `out`
+    if (VEC) {
+      for (int c = W - 4; c >= 0; c -= 4) {
+        const float4 h4 = __ldg(reinterpret_cast<const float4 *>(hp + c));
+        float4 r4;
+        float h;
+        h = h4.w; ret = (c + 3 == W - 1) ? h : ((h >= hn) ? __fadd_rn(h, ret) : h); hn = h; r4.w = __fsub_rn(ret, h);
+        h = h4.z; ret = (h >= hn) ? __fadd_rn(h, ret) : h; hn = h; r4.z = __fsub_rn(ret, h);
+        h = h4.y; ret = (h >= hn) ? __fadd_rn(h, ret) : h; hn = h; r4.y = __fsub_rn(ret, h);
+        h = h4.x; ret = (h >= hn) ? __fadd_rn(h, ret) : h; hn = h; r4.x = __fsub_rn(ret, h);
+        *reinterpret_cast<float4 *>(op + c) = r4;
       }
-      __syncthreads();
-      if (r < nr) {
-        for (int cc = cw - 1; cc >= 0; --cc) {
-          const float h = th[r][cc];
-          if (c0 + cc == W - 1) {
-            ret = h;
-          } else {
-            ret = (h >= hnext) ? __fadd_rn(h, ret) : h;
-          }
-          hnext = h;
-          tr[r][cc] = __fsub_rn(ret, h);
-        }
+    } else {
+      for (int c = W - 1; c >= 0; --c) {
+        const float h = __ldg(hp + c);
+        ret = (c == W - 1) ? h : ((h >= hn) ? __fadd_rn(h, ret) : h);
+        hn = h;
+        op[c] = __fsub_rn(ret, h);
       }
-      __syncthreads();
-      for (int i = threadIdx.x; i < nr * cw; i += AG_R) {
-        const int rr = i / cw, cc = i - rr * cw;
-        out[(row0 + rr) * W + c0 + cc] = tr[rr][cc];
-      }
-      __syncthreads();
     }
     if (mode == 2) return;
   }
-  // ---- forward pass (left aggregate, decode.py:17-28) + combine
-  float hprev = 0.0f;
-  for (int ch = 0; ch < nchunk; ++ch) {
-    const int c0 = ch * AG_CW, cw = min(AG_CW, W - c0);
-    for (int i = threadIdx.x; i < nr * cw; i += AG_R) {
-      const int rr = i / cw, cc = i - rr * cw;
-      th[rr][cc] = heat[(row0 + rr) * W + c0 + cc];
-      tr[rr][cc] = (mode == 0) ? out[(row0 + rr) * W + c0 + cc] : 0.0f;
+  // left aggregate (decode.py:17-28) + combine
+  if (VEC) {
+    for (int c = 0; c < W; c += 4) {
+      const float4 h4 = __ldg(reinterpret_cast<const float4 *>(hp + c));
+      float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mode == 0) rv = *reinterpret_cast<const float4 *>(op + c);
+      float4 o4;
+      float h;
+      h = h4.x; ret = (c == 0) ? h : ((h >= hn) ? __fadd_rn(h, ret) : h); hn = h; o4.x = combine(mode, w, __fsub_rn(ret, h), rv.x, h);
+      h = h4.y; ret = (h >= hn) ? __fadd_rn(h, ret) : h; hn = h; o4.y = combine(mode, w, __fsub_rn(ret, h), rv.y, h);
+      h = h4.z; ret = (h >= hn) ? __fadd_rn(h, ret) : h; hn = h; o4.z = combine(mode, w, __fsub_rn(ret, h), rv.z, h);
+      h = h4.w; ret = (h >= hn) ? __fadd_rn(h, ret) : h; hn = h; o4.w = combine(mode, w, __fsub_rn(ret, h), rv.w, h);
+      *reinterpret_cast<float4 *>(op + c) = o4;
     }
-    __syncthreads();
-    if (r < nr) {
-      for (int cc = 0; cc < cw; ++cc) {
-        const float h = th[r][cc];
-        if (c0 + cc == 0) {
-          ret = h;
-        } else {
-          ret = (h >= hprev) ? __fadd_rn(h, ret) : h;
-        }
-        hprev = h;
-        tr[r][cc] = combine(mode, w, __fsub_rn(ret, h), tr[r][cc], h);
-      }
+  } else {
+    for (int c = 0; c < W; ++c) {
+      const float h = __ldg(hp + c);
+      ret = (c == 0) ? h : ((h >= hn) ? __fadd_rn(h, ret) : h);
+      hn = h;
+      const float rv = (mode == 0) ? op[c] : 0.0f;
+      op[c] = combine(mode, w, __fsub_rn(ret, h), rv, h);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nr * cw; i += AG_R) {
-      const int rr = i / cw, cc = i - rr * cw;
-      out[(row0 + rr) * W + c0 + cc] = tr[rr][cc];
-    }
-    __syncthreads();
   }
 }
 
@@ -134,9 +120,11 @@ int launch_edge_aggregate(const float *heat, float *out, int n, int c, int h, in
   const int mode = (horizontal <= 1) ? 0 : ((horizontal == 2 || horizontal == 4) ? 1 : 2);
   if (rows) {
     const long long nrows = planes * h;
-    const size_t smem = (size_t)2 * AG_R * (AG_CW + 1) * sizeof(float);
-    CNB_CUDA(cudaFuncSetAttribute(k_aggr_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_aggr_rows<<<(unsigned)((nrows + AG_R - 1) / AG_R), AG_R, smem, stream>>>(heat, out, nrows, w, weight, mode);
+    const bool vec = (w % 4 == 0) && ((((uintptr_t)heat | (uintptr_t)out) & 15u) == 0);
+    if (vec)
+      k_aggr_rows<true><<<(unsigned)((nrows + 255) / 256), 256, 0, stream>>>(heat, out, nrows, w, weight, mode);
+    else
+      k_aggr_rows<false><<<(unsigned)((nrows + 255) / 256), 256, 0, stream>>>(heat, out, nrows, w, weight, mode);
   } else {
     const long long blocks = planes * ((w + 127) / 128);
     k_aggr_cols<<<(unsigned)blocks, 128, 0, stream>>>(heat, out, planes, h, w, weight, mode);

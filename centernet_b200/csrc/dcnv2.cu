@@ -479,24 +479,39 @@ static int check_shape(const char *fn, int b, int cin, int h, int w, int cout, i
 
 }  // namespace cnb
 
+namespace cnb {
+size_t dcn_tc_workspace_bytes(int cin, int cout, int dg);
+int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
+                   const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
+                   int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream);
+}
+
 using namespace cnb;
 
 extern "C" {
 
-size_t cnb_dcnv2_workspace_bytes(int, int, int, int, int, int, int, int, int, int, int) {
-  return 0;  // im2col-free: no column / ones scratch (the reference's `columns`, `ones`)
+// No column / ones scratch (the reference's `columns`, `ones`): the workspace only holds the weights
+// re-tiled (TF32 hi/lo split, UMMA layout) for the tensor-core forward.  Passing workspace == NULL
+// (or too small) to cnb_dcnv2_forward selects the fp32 CUDA-core kernel instead.
+size_t cnb_dcnv2_workspace_bytes(int, int cin, int cout, int, int, int kh, int kw, int, int, int, int dg) {
+  if (cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX) return 0;
+  return dcn_tc_workspace_bytes(cin, cout, dg);
 }
 
 int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask, const float *weight,
                       const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw,
                       int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_groups,
-                      void *, size_t, void *stream_) {
+                      void *workspace, size_t workspace_bytes, void *stream_) {
   CNB_REQUIRE(input && offset && mask && weight && output, CNB_EINVAL, "cnb_dcnv2_forward: null pointer");
   DcnShape s;
   int rc = check_shape("cnb_dcnv2_forward", b, cin, h, w, cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h,
                        dil_w, deformable_groups, &s);
   if (rc != CNB_OK) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (workspace && workspace_bytes >= dcn_tc_workspace_bytes(cin, cout, deformable_groups) &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0)
+    return dcn_forward_tc(input, offset, mask, weight, bias, output, b, cin, h, w, cout, kh, kw, stride_h, stride_w,
+                          pad_h, pad_w, dil_h, dil_w, deformable_groups, workspace, stream);
   const long long HWo = (long long)s.Ho * s.Wo;
   const int tiles = (int)((HWo + DCN_TP - 1) / DCN_TP);
   const int nsets = cout > 64 ? 2 : 1;

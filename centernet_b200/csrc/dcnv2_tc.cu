@@ -1,0 +1,314 @@
+// DCNv2 forward with the dense contraction on the 5th-generation tensor cores (tcgen05 / UMMA).
+//
+// Same decomposition as dcnv2.cu (a CTA owns 128 output pixels x 64|128 output channels, the
+// bilinear geometry of every (tap, pixel) is computed once, the sampled column tile of 8 input
+// channels is built in shared memory -- never in HBM), but the contraction
+//     D[128 pixels, Cout_tile] += col[128, 72] * W[Cout_tile, 72]^T
+// is issued by ONE thread as tcgen05.mma.kind::tf32 instructions (UTCHMMA in SASS), A and B both
+// K-major in the canonical no-swizzle shared-memory layout, the accumulator in TMEM (128 lanes x
+// Cout_tile fp32 columns), read back with tcgen05.ld for the bias + store epilogue.
+//
+// Precision: the reference contraction is an fp32 SGEMM (dcn_v2_cuda.c:93-96).  Plain TF32 would
+// miss the 1e-4 bar for K = Cin*9 up to 4608, so every operand is split x = hi + lo with hi = x
+// truncated to TF32 (lo is exact in fp32) and three MMAs are accumulated: hi*hi + hi*lo + lo*hi
+// ("3xTF32"); the dropped lo*lo term and the TF32 rounding of lo are both ~2^-22 relative.
+//
+// The weight tiles are pre-split and pre-tiled once per call by k_dcn_prep_weights into the
+// caller-provided workspace, so every chunk's B operand (hi + lo) arrives by two TMA bulk copies
+// (cp.async.bulk, UBLKCP) that overlap with the sampling of the A tile.
+#include "common.cuh"
+
+namespace cnb {
+
+constexpr int TC_TP = 128;        // pixels per CTA (UMMA M)
+constexpr int TC_CK = 8;          // input channels per chunk
+constexpr int TC_K = 72;          // K per chunk (8 channels x 9 taps, zero padded for smaller kernels)
+constexpr int TC_KC = TC_K / 4;   // 16-byte k-chunks
+constexpr int TC_THREADS = 1024;      // 32 warps: the sampling phase is gather-latency bound, it needs the warps
+constexpr uint32_t TC_LBO = 128;            // bytes between consecutive k-chunks (one 8 x 16 B core matrix)
+constexpr uint32_t TC_SBO = TC_KC * 128;    // bytes between 8-row groups
+constexpr int TC_A_BYTES = TC_TP * TC_K * 4;  // 36864
+
+struct DcnShapeTc {
+  int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo;
+  int co_t;       // output channels per CTA (64 or 128)
+  int n_chunks;   // channel chunks (summed over deformable groups)
+};
+
+struct TapMetaTc {
+  int o[4];
+  float w[4];
+};
+
+__device__ __forceinline__ uint32_t tc_tile_off(int row, int k) {  // byte offset of element (row, k) in a K-major tile
+  return (uint32_t)(row >> 3) * TC_SBO + (uint32_t)(k >> 2) * TC_LBO + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 3) * 4u;
+}
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((TC_LBO >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((TC_SBO >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout_type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// W[Cout][Cin][KT] -> per (cout tile, chunk): hi tile then lo tile, each [co_t][72] in the UMMA layout.
+__global__ void __launch_bounds__(256) k_dcn_prep_weights(const float *__restrict__ w, const DcnShapeTc s,
+                                                          float *__restrict__ ws) {
+  const int KT = s.kh * s.kw;
+  const int cpg = s.Cin / s.dg;
+  const int chunks_pg = (cpg + TC_CK - 1) / TC_CK;
+  const int tile = blockIdx.x;                 // (cout tile, chunk)
+  const int cot = tile / s.n_chunks, ch = tile - cot * s.n_chunks;
+  const int g = ch / chunks_pg, c0 = g * cpg + (ch - g * chunks_pg) * TC_CK;
+  const int ck = min(TC_CK, (g + 1) * cpg - c0);
+  const size_t tile_floats = (size_t)s.co_t * TC_K;
+  unsigned char *hi = reinterpret_cast<unsigned char *>(ws + (size_t)tile * 2 * tile_floats);
+  unsigned char *lo = hi + tile_floats * 4;
+  for (int i = threadIdx.x; i < s.co_t * TC_K; i += blockDim.x) {
+    const int o = i / TC_K, k = i - o * TC_K;
+    const int cl = k / KT, t = k - cl * KT;
+    float v = 0.f;
+    const int oc = cot * s.co_t + o;
+    if (oc < s.Cout && cl < ck && cl < TC_CK) v = w[((size_t)oc * s.Cin + c0 + cl) * KT + t];
+    const float h = tf32_hi(v);
+    *reinterpret_cast<float *>(hi + tc_tile_off(o, k)) = h;
+    *reinterpret_cast<float *>(lo + tc_tile_off(o, k)) = v - h;
+  }
+}
+
+template <int CO_T>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_dcn_forward_tc(const float *__restrict__ x, const float *__restrict__ offset, const float *__restrict__ mask,
+                 const float *__restrict__ wtiles, const float *__restrict__ bias, float *__restrict__ y,
+                 const DcnShapeTc s) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  constexpr int B_BYTES = CO_T * TC_K * 4;
+  unsigned char *a_hi = tc_smem;
+  unsigned char *a_lo = a_hi + TC_A_BYTES;
+  unsigned char *b_hi = a_lo + TC_A_BYTES;
+  unsigned char *b_lo = b_hi + B_BYTES;
+  TapMetaTc *meta = reinterpret_cast<TapMetaTc *>(b_lo + B_BYTES);     // [9][128]
+  __shared__ __align__(8) uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KT = s.kh * s.kw;
+  const long long HWo = (long long)s.Ho * s.Wo, HW = (long long)s.H * s.W;
+  const int tiles = (int)((HWo + TC_TP - 1) / TC_TP);
+  const int b = blockIdx.x / tiles;
+  const long long p_base = (long long)(blockIdx.x - b * tiles) * TC_TP;
+  const int cot = blockIdx.y;
+  const int cpg = s.Cin / s.dg;
+  const int chunks_pg = (cpg + TC_CK - 1) / TC_CK;
+
+  if (tid == 0) {
+    mbar_init(&bar_b, 1);
+    mbar_init(&bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)),
+                 "n"(CO_T));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO_T >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
+
+  int chunk = 0;
+  for (int g = 0; g < s.dg; ++g) {
+    // ---- bilinear geometry of every (tap, pixel) of this deformable group (mask folded into the weights)
+    if (chunk > 0) mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));   // (meta is not read by the MMAs, but keep the order simple)
+    __syncthreads();
+    for (int idx = tid; idx < KT * TC_TP; idx += TC_THREADS) {
+      const int t = idx / TC_TP, pp = idx - t * TC_TP;
+      const long long p = p_base + pp;
+      TapMetaTc mt;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { mt.o[q] = 0; mt.w[q] = 0.f; }
+      if (p < HWo) {
+        const int ho = (int)(p / s.Wo), wo = (int)(p - (long long)ho * s.Wo);
+        const int i = t / s.kw, j = t - i * s.kw;
+        const float *op = offset + ((long long)b * s.dg + g) * 2 * KT * HWo;
+        const float dy = __ldg(op + (2 * t) * HWo + p), dx = __ldg(op + (2 * t + 1) * HWo + p);
+        const float m = __ldg(mask + (((long long)b * s.dg + g) * KT + t) * HWo + p);
+        const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + dy;
+        const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + dx;
+        if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {   // dcn_v2_im2col_cuda.cu:165
+          const float hf = floorf(h_im), wf = floorf(w_im);
+          const int hl = (int)hf, wl = (int)wf;
+          const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+          const int base = hl * s.W + wl;
+          if (hl >= 0 && wl >= 0) { mt.o[0] = base; mt.w[0] = hh * hw * m; }                       // :31-41
+          if (hl >= 0 && wl + 1 <= s.W - 1) { mt.o[1] = base + 1; mt.w[1] = hh * lw * m; }
+          if (hl + 1 <= s.H - 1 && wl >= 0) { mt.o[2] = base + s.W; mt.w[2] = lh * hw * m; }
+          if (hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1) { mt.o[3] = base + s.W + 1; mt.w[3] = lh * lw * m; }
+        }
+      }
+      meta[idx] = mt;
+    }
+    __syncthreads();
+    for (int cc = 0; cc < chunks_pg; ++cc, ++chunk) {
+      const int c0 = g * cpg + cc * TC_CK;
+      const int ck = min(TC_CK, (g + 1) * cpg - c0);
+      // the previous chunk's MMAs must have consumed A and B before they are overwritten
+      if (chunk > 0) mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));
+      if (tid == 0) {  // B operand (hi + lo tiles, contiguous in the workspace): two TMA bulk copies
+        const float *src = wtiles + ((size_t)cot * s.n_chunks + chunk) * 2 * (size_t)CO_T * TC_K;
+        mbar_expect_tx(&bar_b, 2u * B_BYTES);
+        for (uint32_t off = 0; off < 2u * B_BYTES; off += 18432u)
+          bulk_g2s(b_hi + off, reinterpret_cast<const unsigned char *>(src) + off, 18432u, &bar_b);
+      }
+      // ---- A operand: sampled column tile, split into TF32 hi / lo, written in the UMMA layout.
+      //      work item = (pixel, tap, half of the chunk's channels): the (tap, pixel) geometry is read
+      //      once and reused for 4 channels (16 independent gathers in flight per item)
+      for (int idx = tid; idx < TC_TP * KT * 2; idx += TC_THREADS) {
+        const int pp = idx & (TC_TP - 1), r = idx >> 7;       // r = t * 2 + half
+        const int t = r >> 1, half = r & 1;
+        const TapMetaTc mt = meta[t * TC_TP + pp];
+        const float *xp = x + ((long long)b * s.Cin + c0 + half * 4) * HW;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float val = 0.f;
+          if (half * 4 + q < ck) {
+            const float *xc = xp + (long long)q * HW;
+            val = mt.w[0] * __ldg(xc + mt.o[0]);
+            val = fmaf(mt.w[1], __ldg(xc + mt.o[1]), val);
+            val = fmaf(mt.w[2], __ldg(xc + mt.o[2]), val);
+            val = fmaf(mt.w[3], __ldg(xc + mt.o[3]), val);
+          }
+          v[q] = val;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = (half * 4 + q) * KT + t;
+          const float h = tf32_hi(v[q]);
+          const uint32_t off = tc_tile_off(pp, k);
+          *reinterpret_cast<float *>(a_hi + off) = h;
+          *reinterpret_cast<float *>(a_lo + off) = v[q] - h;
+        }
+      }
+      // K rows beyond 8 * KT (kernels smaller than 3x3) stay zero
+      if (KT < 9)
+        for (int idx = tid; idx < TC_TP * (TC_K - 8 * KT); idx += TC_THREADS) {
+          const int pp = idx & (TC_TP - 1), k = 8 * KT + (idx >> 7);
+          *reinterpret_cast<float *>(a_hi + tc_tile_off(pp, k)) = 0.f;
+          *reinterpret_cast<float *>(a_lo + tc_tile_off(pp, k)) = 0.f;
+        }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(&bar_b, (uint32_t)(chunk & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll 1
+        for (int ks = 0; ks < TC_K / 8; ++ks) {   // one UMMA per 8 k (two 16-byte k-chunks), 3 per step (3xTF32)
+          const uint32_t koff = (uint32_t)ks * 2u * TC_LBO;
+          const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
+          const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
+          const uint32_t acc0 = (chunk > 0 || ks > 0) ? 1u : 0u;
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dal), "l"(dbh),
+                       "r"(idesc), "r"(acc0) : "memory");      // lo * hi   (small terms first)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbl),
+                       "r"(idesc), "r"(1u) : "memory");        // hi * lo
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbh),
+                       "r"(idesc), "r"(1u) : "memory");        // hi * hi
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&bar_mma)) : "memory");
+      }
+    }
+  }
+  // ---- epilogue: TMEM -> registers -> bias -> global (coalesced along pixels)
+  mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp < 8) {
+    constexpr int HALF = CO_T / 2;                 // columns per warp group (warps 0-3: first half, 4-7: second)
+    const int q = warp & 3, h = warp >> 2;
+    const long long p = p_base + q * 32 + lane;
+    const uint32_t taddr = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HALF);
+#pragma unroll 1
+    for (int c32 = 0; c32 < HALF; c32 += 32) {
+      uint32_t v[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+          "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr + (uint32_t)c32));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (p < HWo) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int o = cot * CO_T + h * HALF + c32 + j;
+          if (o < s.Cout) {
+            const float bv = bias ? __ldg(bias + o) : 0.f;
+            y[((long long)b * s.Cout + o) * HWo + p] = __uint_as_float(v[j]) + bv;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(CO_T));
+}
+
+static void fill_shape(DcnShapeTc *s, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph,
+                       int pw, int dh, int dw, int dg) {
+  s->B = b; s->Cin = cin; s->H = h; s->W = w; s->Cout = cout; s->kh = kh; s->kw = kw; s->sh = sh; s->sw = sw;
+  s->ph = ph; s->pw = pw; s->dh = dh; s->dw = dw; s->dg = dg;
+  s->Ho = (h + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
+  s->Wo = (w + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+  s->co_t = cout > 64 ? 128 : 64;
+  const int cpg = cin / dg;
+  s->n_chunks = dg * ((cpg + TC_CK - 1) / TC_CK);
+}
+
+size_t dcn_tc_workspace_bytes(int cin, int cout, int dg) {
+  DcnShapeTc s;
+  fill_shape(&s, 1, cin, 8, 8, cout, 3, 3, 1, 1, 1, 1, 1, 1, dg);
+  const int cot = (cout + s.co_t - 1) / s.co_t;
+  return (size_t)cot * s.n_chunks * 2 * s.co_t * TC_K * 4;
+}
+
+// Tensor-core forward.  Requires kh*kw <= 9 (checked by the caller) and a workspace of
+// dcn_tc_workspace_bytes(); enqueues the weight re-tiling kernel + the fused forward.
+int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
+                   const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
+                   int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream) {
+  DcnShapeTc s;
+  fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
+  const int cot = (cout + s.co_t - 1) / s.co_t;
+  float *ws = reinterpret_cast<float *>(workspace);
+  k_dcn_prep_weights<<<cot * s.n_chunks, 256, 0, stream>>>(weight, s, ws);
+  CNB_CHECK_LAUNCH("cnb_dcnv2_forward weight tiles");
+  const long long HWo = (long long)s.Ho * s.Wo;
+  const int tiles = (int)((HWo + TC_TP - 1) / TC_TP);
+  dim3 grid((unsigned)(b * tiles), (unsigned)cot);
+  const size_t smem = 2 * (size_t)TC_A_BYTES + 2 * (size_t)s.co_t * TC_K * 4 + sizeof(TapMetaTc) * 9 * TC_TP;
+  if (s.co_t == 64) {
+    CNB_CUDA(cudaFuncSetAttribute(k_dcn_forward_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dcn_forward_tc<64><<<grid, TC_THREADS, smem, stream>>>(input, offset, mask, ws, bias, output, s);
+  } else {
+    CNB_CUDA(cudaFuncSetAttribute(k_dcn_forward_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dcn_forward_tc<128><<<grid, TC_THREADS, smem, stream>>>(input, offset, mask, ws, bias, output, s);
+  }
+  CNB_CHECK_LAUNCH("cnb_dcnv2_forward (tcgen05)");
+  count_launch(2);
+  return CNB_OK;
+}
+
+}  // namespace cnb

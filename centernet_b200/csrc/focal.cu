@@ -142,17 +142,21 @@ __global__ void __launch_bounds__(FOCAL_THREADS) k_count_pos_dense(const float *
 __global__ void __launch_bounds__(128) k_count_pos_objects(const int32_t *cls, const int32_t *cx, const int32_t *cy,
                                                            const int32_t *rad, const uint8_t *valid, int M, int C,
                                                            int H, int W, FocalAcc *acc) {
+  extern __shared__ int cp_sm[];   // per object: packed key (cls, cy, cx) or -1 when it cannot produce a positive
   const int b = blockIdx.x;
-  int cnt = 0;
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     const size_t o = (size_t)b * M + m;
-    bool ok = valid[o] && cls[o] >= 0 && cls[o] < C && cx[o] >= 0 && cx[o] < W && cy[o] >= 0 && cy[o] < H &&
-              rad[o] >= 0;
-    for (int q = 0; ok && q < m; ++q) {
-      const size_t p = (size_t)b * M + q;
-      if (valid[p] && cls[p] == cls[o] && cx[p] == cx[o] && cy[p] == cy[o] && rad[p] >= 0) ok = false;
-    }
-    cnt += ok ? 1 : 0;
+    const bool ok = valid[o] && cls[o] >= 0 && cls[o] < C && cx[o] >= 0 && cx[o] < W && cy[o] >= 0 && cy[o] < H &&
+                    rad[o] >= 0;
+    cp_sm[m] = ok ? ((cls[o] * H + cy[o]) * W + cx[o]) : -1;
+  }
+  __syncthreads();
+  int cnt = 0;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const int key = cp_sm[m];
+    bool first = key >= 0;
+    for (int q = 0; first && q < m; ++q) first = (cp_sm[q] != key);   // shared memory: cheap O(M^2)
+    cnt += first ? 1 : 0;
   }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&acc->num_pos, (double)cnt);
@@ -365,7 +369,9 @@ int cnb_focal_splat_loss(const float *pred, const int32_t *obj_cls, const int32_
   cudaStream_t stream = (cudaStream_t)stream_;
   FocalAcc *acc = reinterpret_cast<FocalAcc *>(workspace);
   CNB_CUDA(cudaMemsetAsync(acc, 0, sizeof(FocalAcc), stream));
-  k_count_pos_objects<<<b, 128, 0, stream>>>(obj_cls, obj_cx, obj_cy, obj_radius, obj_valid, m, c, h, w, acc);
+  CNB_REQUIRE((long long)c * h * w < (1ll << 31), CNB_EUNSUPPORTED, "cnb_focal_splat_loss: c*h*w must be < 2^31");
+  k_count_pos_objects<<<b, 128, (size_t)m * sizeof(int), stream>>>(obj_cls, obj_cx, obj_cy, obj_radius, obj_valid, m, c, h,
+                                                                    w, acc);
   CNB_CHECK_LAUNCH("cnb_focal_splat_loss count");
   if (logits)
     k_focal_splat<true, false><<<b * c, FOCAL_THREADS, 0, stream>>>(pred, obj_cls, obj_cx, obj_cy, obj_radius,

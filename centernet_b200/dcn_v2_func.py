@@ -6,10 +6,15 @@ delegating to a new-style static autograd Function; the work is done by cnb_dcnv
 cnb_dcnv2_backward (im2col-free, no `ones`/`columns` scratch).  Non-CUDA tensors raise
 NotImplementedError exactly like the reference (:23-24, :41-42).
 """
+import os
+
 import torch
 from torch.autograd import Function
 
-from ._lib import C, f32c, ptr, stream_ptr
+from ._lib import C, f32c, ptr, stream_ptr, workspace
+
+# CNB_DCN_FP32=1 selects the fp32 CUDA-core contraction instead of the tcgen05 (3xTF32) one
+_FORCE_FP32 = os.environ.get("CNB_DCN_FP32", "0") == "1"
 
 
 def _out_hw(h, w, kh, kw, stride, padding, dilation):
@@ -34,8 +39,12 @@ class _DCNv2(Function):
                 tuple(msk.shape) != (n, kt * deformable_groups, ho, wo):
             raise RuntimeError("DCNv2: offset/mask shape does not match the output grid")
         out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
+        ws_bytes = 0 if _FORCE_FP32 else C.dcnv2_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding,
+                                                                 dilation, deformable_groups)
+        ws = workspace(ws_bytes, x.device) if ws_bytes else None
         C.dcnv2_forward(ptr(x), ptr(off), ptr(msk), ptr(w), ptr(b), ptr(out), n, cin, h, wd, cout, kh, kw,
-                        stride, stride, padding, padding, dilation, dilation, deformable_groups, 0, 0, stream_ptr(x))
+                        stride, stride, padding, padding, dilation, dilation, deformable_groups, ptr(ws),
+                        ws.numel() if ws is not None else 0, stream_ptr(x))
         ctx.save_for_backward(x, off, msk, w, b)
         ctx.cfg = (stride, padding, dilation, deformable_groups)
         return out
