@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a)
   u64 thr = 0ull;
   for (long long base = 0; base < total; base += EX_STEP) {
     __syncthreads();
-    if (s_cnt + EX_STEP > EX_CAP) {  // uniform: sort, keep the num_dets best, raise the threshold
-      const int cnt = s_cnt;
+    const int cnt = s_cnt;           // every push of the previous step is in
+    __syncthreads();                 // nobody pushes before everyone has read: the branch is uniform
+    if (cnt + EX_STEP > EX_CAP) {    // sort, keep the num_dets best, raise the threshold
       const int n = np2(cnt);
       for (int t = cnt + tid; t < n; t += blockDim.x) buf[t] = 0ull;
       __syncthreads();

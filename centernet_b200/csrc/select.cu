@@ -725,7 +725,9 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
         }
         __syncthreads();
         for (int b2 = base; b2 < end; b2 += 32) {
-          if (s_cnt[0] + 1024 > SEL_CAP) thr64 = cta_prune(buf, s_cnt, K);
+          const bool full_soon = s_cnt[0] + 1024 > SEL_CAP;   // pushes of the previous step are complete
+          __syncthreads();                                     // ...and none of this step start before all have read
+          if (full_soon) thr64 = cta_prune(buf, s_cnt, K);
           const int word = b2 + (tid >> 5);
           if (word < end && ((masks[word] >> (tid & 31)) & 1u)) {
             const u64 key = make(word, tid & 31);
@@ -837,6 +839,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
     __syncthreads();
     const uint32_t tb = *s_thr;
+    const bool fits = s_cnt[0] <= SEL_CAP;       // read once here, while nobody modifies it
     const int cnt = min(s_cnt[0], SEL_CAP);
     u64 mine[SEL_CAP / SEL_THREADS];
 #pragma unroll
@@ -846,11 +849,11 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     }
     __syncthreads();
     if (tid == 0) {
-      if (s_cnt[0] <= SEL_CAP) s_cnt[0] = 0;   // an overflowed buffer stays flagged; flush rescans
+      if (fits) s_cnt[0] = 0;                  // an overflowed buffer stays flagged; flush rescans
       if (slot_idx >= 0) s_flag[slot_idx] = 0;
     }
     __syncthreads();
-    if (s_cnt[0] == 0) {
+    if (fits) {
 #pragma unroll
       for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j)
         if (mine[j] != 0ull && key_bits(mine[j]) >= tb) buf[atomicAdd(&s_cnt[0], 1)] = mine[j];
@@ -880,7 +883,9 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       for (long long p = lo; p < hi; ++p) {
         const int c = (int)(p - (long long)img * C);
         for (int base = 0; base < HW; base += SEL_THREADS) {
-          if (s_cnt[0] + SEL_THREADS > SEL_CAP) thr64 = cta_prune(buf, s_cnt, K);
+          const bool full_soon = s_cnt[0] + SEL_THREADS > SEL_CAP;   // previous step's pushes are complete
+          __syncthreads();                                            // uniform branch: no push before all have read
+          if (full_soon) thr64 = cta_prune(buf, s_cnt, K);
           const long long flat = (long long)c * HW + base + tid;
           float v = nms_value<true>(ibase, C, 128, 128, flat);
           if (pl.clamp_one) v = fminf(v, 1.0f);

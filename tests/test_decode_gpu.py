@@ -158,6 +158,26 @@ def test_large_k_and_overflow_path():
     np.testing.assert_array_equal(got[..., 4:], want[..., 4:])
 
 
+@pytest.mark.parametrize("B,C", [(4, 80), (64, 80), (3, 7)])
+def test_hot_kernel_overflow_rescan(B, C):
+    """Adversarial for the running threshold: every plane is brighter than all planes before it, so the
+    threshold is always stale, the key buffer overflows between rendezvous points and the exact
+    per-image rebuild (select.cu flush -> rescan) has to produce the answer."""
+    from centernet_b200 import decode as D
+    H = W = 128
+    K = 100
+    g = torch.Generator(device="cuda").manual_seed(99 + B)
+    base = torch.rand(B, C, H, W, device="cuda", generator=g)
+    ramp = torch.linspace(0.01, 0.99, C, device="cuda").view(1, C, 1, 1)
+    heat = (base * 0.01 + ramp).contiguous()
+    wh = torch.rand(B, 2, H, W, device="cuda", generator=g) * 8
+    dets = D.ctdet_decode(heat, wh, K=K)
+    hmax = torch.nn.functional.max_pool2d(heat, 3, stride=1, padding=1)
+    ref_s, ref_i = torch.topk((heat * (hmax == heat).float()).view(B, -1), K)
+    assert torch.equal(ref_s, dets[..., 4])
+    assert torch.equal(ref_i // (H * W), dets[..., 5].long())
+
+
 def test_full_size_properties():
     """BASELINE configs[1] size (B=64): oracle too slow for every run, so check size-independent
     properties: sorted scores, every detection is a 3x3 peak with score == heat at (cls, y, x),
