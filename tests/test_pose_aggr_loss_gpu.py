@@ -68,7 +68,7 @@ def test_golden_aggregate():
     np.testing.assert_array_equal(D._v_aggregate(heat, 0.1).cpu().numpy(), g["v"])
 
 
-@pytest.mark.parametrize("B,C,H,W", [(2, 80, 128, 128), (1, 3, 70, 300), (2, 2, 5, 7)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 80, 128, 128), (1, 3, 70, 300), (2, 2, 5, 7), (1, 2, 33, 516), (1, 1, 600, 36)])
 def test_aggregate_vs_oracle(B, C, H, W):
     from centernet_b200 import decode as D
     heat = noise(B, C, H, W, 9, bias=0.5)
@@ -77,6 +77,8 @@ def test_aggregate_vs_oracle(B, C, H, W):
     np.testing.assert_array_equal(D._v_aggregate(d, 0.1).cpu().numpy(), O.v_aggregate(heat, 0.1))
     np.testing.assert_array_equal(D._left_aggregate(d).cpu().numpy(), O.left_aggregate(heat))
     np.testing.assert_array_equal(D._bottom_aggregate(d).cpu().numpy(), O.bottom_aggregate(heat))
+    np.testing.assert_array_equal(D._right_aggregate(d).cpu().numpy(), O.right_aggregate(heat))
+    np.testing.assert_array_equal(D._top_aggregate(d).cpu().numpy(), O.top_aggregate(heat))
     np.testing.assert_array_equal(d.cpu().numpy(), heat)
 
 
