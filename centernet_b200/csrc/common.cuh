@@ -79,17 +79,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Waits with a watchdog: a protocol bug must surface as a loud failure (message + trap, which the host
-// sees as a launch error), never as a kernel that spins forever.  ~2 s at 2 GHz.
+// Waits with a watchdog: a protocol bug must surface as a loud failure (trap -> the host sees a launch
+// error on its next CUDA call), never as a kernel that spins forever.  ~2 s at 2 GHz.  No printf here:
+// a device printf in the wait path costs the hot kernel registers and a stack frame.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("centernet_b200 watchdog: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (UBLKCP in SASS).

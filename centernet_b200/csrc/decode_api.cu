@@ -136,6 +136,14 @@ static RawTopk carve_raw(char *p, long long n) {
 
 using namespace cnb;
 
+// out = 1 / (1 + exp(-x)), the expression of torch's CUDA sigmoid (4 elements per thread)
+__global__ void __launch_bounds__(256) k_sigmoid(const float *__restrict__ x, float *__restrict__ out, long long n) {
+  const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i0 + j < n) out[i0 + j] = 1.0f / (1.0f + expf(-x[i0 + j]));
+}
+
 extern "C" {
 
 int cnb_nms(const float *heat, float *out, int n, int c, int h, int w, void *stream) {
@@ -209,6 +217,51 @@ int cnb_ctdet_decode(const float *heat, const float *wh, const float *reg, int c
               "cnb_ctdet_decode: workspace %zu < %zu", workspace_bytes, select_workspace_bytes(pl));
   FinalizeOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, wh, reg, cat_spec_wh, dets};
   return run_select(heat, pl, out, workspace, (cudaStream_t)stream);
+}
+
+/* N1: ctdet_decode on the head's raw logits, sigmoid fused (detectors/ctdet.py:31 +
+ * models/decode.py:464-495).  Hot geometry: the selection kernel works in logit space and applies
+ * the sigmoid only to the few candidates; other geometries materialise the heat map once in the
+ * workspace and take the normal path. */
+size_t cnb_ctdet_logits_workspace_bytes(const float *hm_logits, int b, int c, int h, int w, int k) {
+  SelectPlan pl;
+  if (make_select_plan(hm_logits, b, c, h, w, k, 1, &pl) != CNB_OK) return 0;
+  size_t n = select_workspace_bytes(pl);
+  if (!pl.hot) n = align_up(n, 256) + align_up((size_t)b * c * h * w * 4, 256);
+  return n;
+}
+
+int cnb_ctdet_decode_logits(const float *hm_logits, const float *wh, const float *reg, int cat_spec_wh, int b, int c,
+                            int h, int w, int k, float *dets, void *workspace, size_t workspace_bytes, void *stream) {
+  CNB_REQUIRE(hm_logits && wh && dets && workspace, CNB_EINVAL, "cnb_ctdet_decode_logits: null pointer");
+  SelectPlan pl;
+  int rc = make_select_plan(hm_logits, b, c, h, w, k, 1, &pl);
+  if (rc != CNB_OK) return rc;
+  const size_t need = cnb_ctdet_logits_workspace_bytes(hm_logits, b, c, h, w, k);
+  CNB_REQUIRE(workspace_bytes >= need, CNB_EWORKSPACE, "cnb_ctdet_decode_logits: workspace %zu < %zu", workspace_bytes,
+              need);
+  FinalizeOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, wh, reg, cat_spec_wh, dets};
+  if (pl.hot) {
+    pl.logits = 1;
+    return run_select(hm_logits, pl, out, workspace, (cudaStream_t)stream);
+  }
+  float *heat = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align_up(select_workspace_bytes(pl), 256));
+  const long long n = (long long)b * c * h * w;
+  k_sigmoid<<<(unsigned)((n + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(hm_logits, heat, n);
+  CNB_CHECK_LAUNCH("cnb_ctdet_decode_logits sigmoid");
+  count_launch();
+  rc = make_select_plan(heat, b, c, h, w, k, 1, &pl);
+  if (rc != CNB_OK) return rc;
+  return run_select(heat, pl, out, workspace, (cudaStream_t)stream);
+}
+
+int cnb_sigmoid(const float *x, float *out, long long n, void *stream) {
+  CNB_REQUIRE(x && out && n >= 0, CNB_EINVAL, "cnb_sigmoid: bad argument");
+  if (n == 0) return CNB_OK;
+  k_sigmoid<<<(unsigned)((n + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+  CNB_CHECK_LAUNCH("cnb_sigmoid");
+  count_launch();
+  return CNB_OK;
 }
 
 int cnb_ddd_decode(const float *heat, const float *rot, const float *depth, const float *dim, const float *wh,

@@ -62,6 +62,18 @@ PYBIND11_MODULE(_C, m) {
                            ptr<float>(dets), ptr<void>(ws), wsb, ptr<void>(stream)),
           "cnb_ctdet_decode");
   });
+  m.def("ctdet_logits_workspace_bytes", [](P hm, int b, int c, int h, int w, int k) {
+    return cnb_ctdet_logits_workspace_bytes(ptr<const float>(hm), b, c, h, w, k);
+  });
+  m.def("ctdet_decode_logits", [](P hm, P wh, P reg, int cat, int b, int c, int h, int w, int k, P dets, P ws,
+                                  size_t wsb, P stream) {
+    check(cnb_ctdet_decode_logits(ptr<const float>(hm), ptr<const float>(wh), ptr<const float>(reg), cat, b, c, h, w,
+                                  k, ptr<float>(dets), ptr<void>(ws), wsb, ptr<void>(stream)),
+          "cnb_ctdet_decode_logits");
+  });
+  m.def("sigmoid", [](P x, P out, long long n, P stream) {
+    check(cnb_sigmoid(ptr<const float>(x), ptr<float>(out), n, ptr<void>(stream)), "cnb_sigmoid");
+  });
   m.def("ddd_decode", [](P heat, P rot, P depth, P dim, P wh, P reg, int b, int c, int h, int w, int k, P dets, P ws,
                          size_t wsb, P stream) {
     check(cnb_ddd_decode(ptr<const float>(heat), ptr<const float>(rot), ptr<const float>(depth),

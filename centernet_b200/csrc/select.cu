@@ -208,12 +208,39 @@ __device__ __forceinline__ void update_threshold(const int *fine, const int *coa
   if (lane == 0) *s_thr = bits;
 }
 
+// ------------------------------------------------------------------ logits input (fused sigmoid)
+// The same expression torch's CUDA sigmoid evaluates for float (1 / (1 + exp(-x)), libdevice expf,
+// IEEE division; this library is built without fast-math), so scores are bit-identical to
+// `hm.sigmoid_()` (detectors/ctdet.py:31).  tests/test_logits_gpu.py checks both the bit identity
+// and that the function is monotone non-decreasing over every float - the property the logits path
+// relies on: the 3x3 maximum of the heat map is the sigmoid of the 3x3 maximum of the logits.
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Conservative lower bound (in logit space) of a score threshold given as fp32 bits.
+__device__ __forceinline__ float logit_lower_bound(uint32_t score_bits) {
+  if (score_bits == 0u) return CNB_NEG_INF;
+  const float t = __uint_as_float(score_bits);
+  if (!(t >= 1e-30f)) return CNB_NEG_INF;
+  const float l = __logf(t) - __logf(fmaxf(1.0f - t, 1e-8f));
+  return l - (0.002f + 0.002f * fabsf(l));
+}
+// How far below the 3x3 logit maximum M a pixel can sit and still share M's fp32 sigmoid (8 ulp of
+// slack on top of the derivative bound; saturated / denormal ends: always compare).
+__device__ __forceinline__ float collide_margin(float M) {
+  if (M > 12.0f || M < -80.0f) return __int_as_float(0x7f800000);
+  if (M > 8.0f) return 0.25f;
+  if (M > 4.0f) return 4e-3f;
+  if (M > 0.0f) return 1e-4f;
+  return 7.62939453125e-6f;  // 2^-17
+}
+
 // ------------------------------------------------------------------ finalize (shared by both paths)
 // v'(i): the reference's heat*keep value of flat pixel i (keep only in NMS mode).
 template <bool NMS>
-__device__ __forceinline__ float nms_value(const float *__restrict__ img, int C, int H, int W, long long i) {
+__device__ __forceinline__ float nms_value(const float *__restrict__ img, int C, int H, int W, long long i,
+                                           bool logits = false) {
   const float v = img[i];
-  if (!NMS) return v;
+  if (!NMS) return logits ? sigmoid_ref(v) : v;
   const long long HW = (long long)H * W;
   const long long c = i / HW, sp = i - c * HW;
   const int y = (int)(sp / W), x = (int)(sp - (long long)y * W);
@@ -227,6 +254,10 @@ __device__ __forceinline__ float nms_value(const float *__restrict__ img, int C,
       if (xx < 0 || xx >= W) continue;
       m = fmaxf(m, pl[(long long)yy * W + xx]);
     }
+  }
+  if (logits) {  // monotone sigmoid: max of the heat neighbourhood == sigmoid(max of the logits)
+    const float sv = sigmoid_ref(v);
+    return (m == v || sigmoid_ref(m) == sv) ? sv : 0.0f;
   }
   return (m == v) ? v : 0.0f;
 }
@@ -243,7 +274,7 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
   for (long long base = 0; base < N && found < need; base += G::n()) {
     const long long i = base + tid;
     bool pred = false;
-    if (i < N) pred = (nms_value<NMS>(img, pl.C, pl.H, pl.W, i) == 0.0f);
+    if (i < N) pred = (nms_value<NMS>(img, pl.C, pl.H, pl.W, i, pl.logits != 0) == 0.0f);
     const uint32_t bal = __ballot_sync(0xffffffffu, pred);
     if (lane == 0) s_tmp[warp] = __popc(bal);
     G::sync();
@@ -264,7 +295,7 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
   while (found < need) {
     u64 best = 0ull;
     for (long long i = tid; i < N; i += G::n()) {
-      const float v = nms_value<NMS>(img, pl.C, pl.H, pl.W, i);
+      const float v = nms_value<NMS>(img, pl.C, pl.H, pl.W, i, pl.logits != 0);
       if (v < 0.0f) {
         const u64 key = ((u64)(~__float_as_uint(v)) << 32) | (u64)(0xffffffffu - (uint32_t)i);
         if (key < prev && key > best) best = key;
@@ -765,6 +796,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <bool LOGITS>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict__ cand, int *__restrict__ cand_cnt,
              int *__restrict__ img_done, uint32_t *__restrict__ cand_thr, const FinalizeOut fout) {
@@ -777,6 +809,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   uint64_t *full = reinterpret_cast<uint64_t *>(unused_masks + SEL_MASK_WORDS);
   int *s_cnt = reinterpret_cast<int *>(full + SEL_STAGES);   // [0] count [1] overflow [2] last flag [3] compaction
   uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_cnt + 4);
+  float *s_tl = reinterpret_cast<float *>(s_cnt + 5);        // LOGITS: logit-space lower bound of *s_thr
   __shared__ int s_arr[SEL_STAGES];                          // warps done with the stage (last one re-arms it)
   __shared__ int s_flag[4];                                  // compaction rendezvous requested for unit (u & 3)
   __shared__ int s_tmp[32];
@@ -804,7 +837,13 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     if (tid == 0) {
       s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
       *s_thr = 0u;
+      *s_tl = CNB_NEG_INF;
     }
+  };
+  // one warp: refresh the histogram threshold (and its logit-space image)
+  auto refresh_thr = [&]() {
+    update_threshold(fine, coarse, lane, K, s_thr);
+    if (LOGITS && lane == 0) *s_tl = logit_lower_bound(*s_thr);
   };
 
   if (tid == 0) {
@@ -833,10 +872,20 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     else s_cnt[1] = 1;
   };
 
+  // LOGITS: pixel with logit b whose 3x3 logit maximum is M
+  auto try_push_logit = [&](float b, float M, uint32_t flat) {
+    bool pk = (b == M);
+    if (!pk && (M - b) <= collide_margin(M)) pk = (sigmoid_ref(b) == sigmoid_ref(M));
+    if (pk) {
+      const float sv = sigmoid_ref(b);
+      if (sv > 0.0f) push(sv, flat);
+    }
+  };
+
   // ---- CTA-wide compaction of the key buffer against the current threshold (rendezvous, rare)
   auto compact = [&](int slot_idx) {
     __syncthreads();
-    if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+    if (warp == 0) refresh_thr();
     __syncthreads();
     const uint32_t tb = *s_thr;
     const bool fits = s_cnt[0] <= SEL_CAP;       // read once here, while nobody modifies it
@@ -887,7 +936,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
           __syncthreads();                                            // uniform branch: no push before all have read
           if (full_soon) thr64 = cta_prune(buf, s_cnt, K);
           const long long flat = (long long)c * HW + base + tid;
-          float v = nms_value<true>(ibase, C, 128, 128, flat);
+          float v = nms_value<true>(ibase, C, 128, 128, flat, LOGITS);
           if (pl.clamp_one) v = fminf(v, 1.0f);
           if (v > 0.0f) {
             const u64 key = make_key(__float_as_uint(v), (uint32_t)flat);
@@ -901,7 +950,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     } else {
       if (s_cnt[0] > pl.seg_cap) compact(-1);     // drop everything below the histogram threshold (>= K survive)
       else {
-        if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+        if (warp == 0) refresh_thr();
         __syncthreads();
       }
       const int cnt = s_cnt[0];
@@ -963,12 +1012,26 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       if (i < i_lo || i >= i_hi) continue;   // warp-uniform (bootstrap sweeps a row subset)
       // threshold >= smallest positive float, so `b == max(.., thr)` also rejects b <= 0; it is
       // re-read per row (one broadcast LDS): fresher threshold = fewer pushes
-      const float thr_f = __uint_as_float(use_thr ? max(*(volatile uint32_t *)s_thr, 1u) : 1u);
       const float4 a = r_[i], b = r_[i + 1], cc = r_[i + 2];
       const float v0 = fmax3(a.x, b.x, cc.x), v1 = fmax3(a.y, b.y, cc.y);
       const float v2 = fmax3(a.z, b.z, cc.z), v3 = fmax3(a.w, b.w, cc.w);
       const float l = __shfl_up_sync(0xffffffffu, v3, 1) + edge_l;
       const float r = __shfl_down_sync(0xffffffffu, v0, 1) + edge_r;
+      if (LOGITS) {
+        // logit space: one compare per pixel against the logit image of the threshold; the (rare)
+        // survivors are peak-tested exactly: b is a heat peak iff sigmoid(b) == sigmoid(3x3 max)
+        const float tl = use_thr ? *(volatile float *)s_tl : NI;
+        const bool q0 = b.x >= tl, q1 = b.y >= tl, q2 = b.z >= tl, q3 = b.w >= tl;
+        if (q0 | q1 | q2 | q3) {
+          const uint32_t f = fbase + (uint32_t)(i * 128);
+          if (q0) try_push_logit(b.x, fmax3(l, v0, v1), f);
+          if (q1) try_push_logit(b.y, fmax3(v0, v1, v2), f + 1);
+          if (q2) try_push_logit(b.z, fmax3(v1, v2, v3), f + 2);
+          if (q3) try_push_logit(b.w, fmax3(v2, v3, r), f + 3);
+        }
+        continue;
+      }
+      const float thr_f = __uint_as_float(use_thr ? max(*(volatile uint32_t *)s_thr, 1u) : 1u);
       const float m01 = fmaxf(v0, v1), m23 = fmaxf(v2, v3);
       const bool q0 = (b.x == fmax3(l, m01, thr_f));
       const bool q1 = (b.y == fmax3(m01, v2, thr_f));
@@ -1003,18 +1066,18 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       // threshold is refreshed once more, so unit 1 already sees the K-th best of a whole plane.
       sweep(st, c, false, 0, 1);
       __syncthreads();
-      if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+      if (warp == 0) refresh_thr();
       __syncthreads();
       sweep(st, c, true, 1, 4);
       __syncthreads();
-      if (warp == 0) update_threshold(fine, coarse, lane, K, s_thr);
+      if (warp == 0) refresh_thr();
       __syncthreads();
       fresh = false;
       t_boot += clock64() - t0;
     } else {
       sweep(st, c, true, 0, 4);
     }
-    if (warp == (u & (SEL_WARPS - 1))) update_threshold(fine, coarse, lane, K, s_thr);  // partial counts are valid too
+    if (warp == (u & (SEL_WARPS - 1))) refresh_thr();  // partial counts are valid too
     __syncwarp();
     if (first) {
       // last warp to finish this stage re-arms it (no waiting): TMA load of unit u+3
@@ -1093,6 +1156,7 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   CNB_REQUIRE((long long)C * H * W < (1ll << 32), CNB_EUNSUPPORTED, "top-k: c*h*w must be < 2^32");
   pl->n_img = n_img; pl->C = C; pl->H = H; pl->W = W; pl->K = K; pl->nms = nms;
   pl->clamp_one = 0;
+  pl->logits = 0;
   pl->dbg = t_dbg;
   pl->Wp = (W + 3) / 4 * 4;
   pl->ncb = (W + 127) / 128;
@@ -1188,10 +1252,12 @@ static int launch_select(const float *src, const SelectPlan &pl, const FinalizeO
     int dev = 0;
     cudaGetDevice(&dev);
     if (hot_dev != dev) {
-      CNB_CUDA(cudaFuncSetAttribute(k_select_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      CNB_CUDA(cudaFuncSetAttribute(k_select_hot<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      CNB_CUDA(cudaFuncSetAttribute(k_select_hot<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       hot_dev = dev;
     }
-    k_select_hot<<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, thr, out);
+    if (pl.logits) k_select_hot<true><<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, thr, out);
+    else k_select_hot<false><<<pl.n_cta, SEL_THREADS, smem1, stream>>>(src, pl, cand, cnt, done, thr, out);
     CNB_CHECK_LAUNCH("select stage 1 (hot)");
     count_launch();
     rc = CNB_OK;

@@ -28,6 +28,7 @@ struct SelectPlan {
   int max_slots;  // candidate segments an image can receive (<= CTAs overlapping it)
   int use_tma;
   int nms;
+  int logits;     // src holds pre-sigmoid logits; scores are sigmoid(src) (hot geometry only, detectors/ctdet.py:31)
   int clamp_one;  // order by min(score, 1): exct_decode clamps the NMS'd maps before _topk (decode.py:299-302)
   int fused_finalize;  // last CTA of an image merges its segments inside stage 1
   int seg_cap;    // keys per candidate segment (>= K; the hot kernel delivers unsorted supersets)

@@ -134,6 +134,35 @@ def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100):
     return dets
 
 
+def ctdet_decode_from_logits(hm, wh, reg=None, cat_spec_wh=False, K=100):
+    """`ctdet_decode(hm.sigmoid_(), wh, reg, ...)` (detectors/ctdet.py:30-45) in one launch, reading the
+    head's raw logits: the selection runs in logit space (the sigmoid is monotone) and only the
+    candidates are pushed through 1/(1+exp(-x)).  Scores are bit-identical to torch's CUDA sigmoid,
+    indices / classes / boxes identical to ctdet_decode on that heat map; `hm` is not modified."""
+    require_cuda(hm, wh, reg, what="ctdet_decode_from_logits")
+    hm, wh, reg = f32c(hm), f32c(wh), f32c(reg)
+    b, c, h, w = _dims(hm)
+    want = 2 * c if cat_spec_wh else 2
+    if wh.shape[0] != b or wh.shape[1] != want or tuple(wh.shape[2:]) != (h, w):
+        raise RuntimeError("ctdet_decode_from_logits: wh must be [%d, %d, %d, %d], got %s" % (b, want, h, w, tuple(wh.shape)))
+    if reg is not None and tuple(reg.shape) != (b, 2, h, w):
+        raise RuntimeError("ctdet_decode_from_logits: reg must be [%d, 2, %d, %d], got %s" % (b, h, w, tuple(reg.shape)))
+    dets = torch.empty((b, K, 6), dtype=torch.float32, device=hm.device)
+    ws = workspace(C.ctdet_logits_workspace_bytes(ptr(hm), b, c, h, w, K), hm.device)
+    C.ctdet_decode_logits(ptr(hm), ptr(wh), ptr(reg), int(bool(cat_spec_wh)), b, c, h, w, K, ptr(dets), ptr(ws),
+                          ws.numel(), stream_ptr(hm))
+    return dets
+
+
+def sigmoid(x):
+    """Bare sigmoid (detectors/ctdet.py:31) through the library's own kernel; returns a new tensor."""
+    require_cuda(x, what="sigmoid")
+    x = f32c(x)
+    out = torch.empty_like(x)
+    C.sigmoid(ptr(x), ptr(out), x.numel(), stream_ptr(x))
+    return out
+
+
 # ------------------------------------------------------------------ decode.py:426-462
 def ddd_decode(heat, rot, depth, dim, wh=None, reg=None, K=40):
     require_cuda(heat, rot, depth, dim, wh, reg, what="ddd_decode")

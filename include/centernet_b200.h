@@ -89,6 +89,21 @@ int cnb_ctdet_decode(const float *heat, const float *wh, const float *reg, int c
                      int b, int c, int h, int w, int k, float *dets,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------- N1: ctdet_decode with fused sigmoid
+ * Replaces `hm = output['hm'].sigmoid_(); ctdet_decode(hm, wh, reg, ...)`
+ * (detectors/ctdet.py:30-45): hm_logits [b,c,h,w] is the head's raw output.
+ * Scores are bit-identical to torch's CUDA sigmoid of the logits, indices and
+ * classes identical to cnb_ctdet_decode on that heat map.  The workspace query
+ * takes the logits pointer because its alignment decides the code path. */
+size_t cnb_ctdet_logits_workspace_bytes(const float *hm_logits, int b, int c, int h, int w, int k);
+int cnb_ctdet_decode_logits(const float *hm_logits, const float *wh, const float *reg, int cat_spec_wh,
+                            int b, int c, int h, int w, int k, float *dets,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* out[i] = 1 / (1 + exp(-x[i])): the bare `sigmoid_()` of detectors/ctdet.py:31, the very expression the
+ * fused path applies to its candidates (exposed so tests can pin it against torch and prove it monotone). */
+int cnb_sigmoid(const float *x, float *out, long long n, void *stream);
+
 /* ------------------------------------------------------------ A9: ddd_decode
  * models/decode.py:426-462.  rot [b,8,h,w], depth [b,1,h,w], dim [b,3,h,w],
  * wh/reg [b,2,h,w] or NULL -> dets [b,k,18] (16 when wh == NULL). */
