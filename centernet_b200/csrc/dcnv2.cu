@@ -480,7 +480,7 @@ static int check_shape(const char *fn, int b, int cin, int h, int w, int cout, i
 }  // namespace cnb
 
 namespace cnb {
-size_t dcn_tc_workspace_bytes(int cin, int cout, int dg);
+size_t dcn_tc_workspace_bytes(int b, int cin, int h, int w, int cout, int dg);
 int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
                    const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
                    int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream);
@@ -490,12 +490,12 @@ using namespace cnb;
 
 extern "C" {
 
-// No column / ones scratch (the reference's `columns`, `ones`): the workspace only holds the weights
-// re-tiled (TF32 hi/lo split, UMMA layout) for the tensor-core forward.  Passing workspace == NULL
+// No column / ones scratch (the reference's `columns`, `ones`): the workspace holds the weights re-tiled
+// (TF32 hi/lo split, UMMA layout) and a channels-last copy of the input for the tensor-core forward.  Passing workspace == NULL
 // (or too small) to cnb_dcnv2_forward selects the fp32 CUDA-core kernel instead.
-size_t cnb_dcnv2_workspace_bytes(int, int cin, int cout, int, int, int kh, int kw, int, int, int, int dg) {
-  if (cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX) return 0;
-  return dcn_tc_workspace_bytes(cin, cout, dg);
+size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw, int, int, int, int dg) {
+  if (b <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX) return 0;
+  return dcn_tc_workspace_bytes(b, cin, h, w, cout, dg);
 }
 
 int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask, const float *weight,
@@ -508,7 +508,7 @@ int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask
                        dil_w, deformable_groups, &s);
   if (rc != CNB_OK) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (workspace && workspace_bytes >= dcn_tc_workspace_bytes(cin, cout, deformable_groups) &&
+  if (workspace && workspace_bytes >= dcn_tc_workspace_bytes(b, cin, h, w, cout, deformable_groups) &&
       (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0)
     return dcn_forward_tc(input, offset, mask, weight, bias, output, b, cin, h, w, cout, kh, kw, stride_h, stride_w,
                           pad_h, pad_w, dil_h, dil_w, deformable_groups, workspace, stream);

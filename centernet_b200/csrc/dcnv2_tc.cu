@@ -13,6 +13,12 @@
 // truncated to TF32 (lo is exact in fp32) and three MMAs are accumulated: hi*hi + hi*lo + lo*hi
 // ("3xTF32"); the dropped lo*lo term and the TF32 rounding of lo are both ~2^-22 relative.
 //
+// Sampling: the input is first re-laid channels-last (k_dcn_nhwc: [B][H*W][chunk][8 channels], one
+// coalesced pass), so one bilinear corner of a (pixel, tap) brings the 8 channels of the chunk with two
+// 16-byte loads from one 32-byte sector -- the NCHW layout needs 8 scalar loads from 8 different planes.
+// A work item is a (pixel, tap): 8 vector gathers, 32 FMAs, the TF32 split, four 16-byte stores into
+// the UMMA tile (K is ordered tap-major, k = tap * 8 + channel, so the 8 channels are two k-chunks).
+//
 // The weight tiles are pre-split and pre-tiled once per call by k_dcn_prep_weights into the
 // caller-provided workspace, so every chunk's B operand (hi + lo) arrives by two TMA bulk copies
 // (cp.async.bulk, UBLKCP) that overlap with the sampling of the A tile.
@@ -21,21 +27,24 @@
 namespace cnb {
 
 constexpr int TC_TP = 128;        // pixels per CTA (UMMA M)
-constexpr int TC_CK = 8;          // input channels per chunk
-constexpr int TC_K = 72;          // K per chunk (8 channels x 9 taps, zero padded for smaller kernels)
+constexpr int TC_CB = 32;         // input channels per chunk = one 128-byte line of the channels-last copy
+constexpr int TC_TG = 1;          // taps per chunk
+constexpr int TC_NTG = 9;         // tap groups (3x3 kernel)
+constexpr int TC_K = TC_CB * TC_TG;   // 32: K per chunk, k = channel_local
 constexpr int TC_KC = TC_K / 4;   // 16-byte k-chunks
-constexpr int TC_THREADS = 1024;      // 32 warps: the sampling phase is gather-latency bound, it needs the warps
+constexpr int TC_THREADS = 512;       // 16 warps, two CTAs per SM: one samples while the other's MMAs run
 constexpr uint32_t TC_LBO = 128;            // bytes between consecutive k-chunks (one 8 x 16 B core matrix)
 constexpr uint32_t TC_SBO = TC_KC * 128;    // bytes between 8-row groups
-constexpr int TC_A_BYTES = TC_TP * TC_K * 4;  // 36864
+constexpr int TC_A_BYTES = TC_TP * TC_K * 4;  // 16384
 
 struct DcnShapeTc {
   int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo;
   int co_t;       // output channels per CTA (64 or 128)
-  int n_chunks;   // channel chunks (summed over deformable groups)
+  int cbs_pg;     // 32-channel blocks per deformable group
+  int n_chunks;   // chunks = dg * 9 taps * cbs_pg
 };
 
-struct TapMetaTc {
+struct __align__(16) TapMetaTc {
   int o[4];
   float w[4];
 };
@@ -53,34 +62,70 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr) {
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// W[Cout][Cin][KT] -> per (cout tile, chunk): hi tile then lo tile, each [co_t][72] in the UMMA layout.
+// W[Cout][Cin][KT] -> per (cout tile, chunk): hi tile then lo tile, each [co_t][32] in the UMMA layout.
+// chunk = (group g, tap t, channel block cbi) in that nesting order; k = channel within the block.
 __global__ void __launch_bounds__(256) k_dcn_prep_weights(const float *__restrict__ w, const DcnShapeTc s,
                                                           float *__restrict__ ws) {
   const int KT = s.kh * s.kw;
   const int cpg = s.Cin / s.dg;
-  const int chunks_pg = (cpg + TC_CK - 1) / TC_CK;
   const int tile = blockIdx.x;                 // (cout tile, chunk)
   const int cot = tile / s.n_chunks, ch = tile - cot * s.n_chunks;
-  const int g = ch / chunks_pg, c0 = g * cpg + (ch - g * chunks_pg) * TC_CK;
-  const int ck = min(TC_CK, (g + 1) * cpg - c0);
+  const int per_g = TC_NTG * s.cbs_pg;
+  const int g = ch / per_g, r = ch - g * per_g;
+  const int tg = r / s.cbs_pg, cbi = r - tg * s.cbs_pg;
   const size_t tile_floats = (size_t)s.co_t * TC_K;
   unsigned char *hi = reinterpret_cast<unsigned char *>(ws + (size_t)tile * 2 * tile_floats);
   unsigned char *lo = hi + tile_floats * 4;
   for (int i = threadIdx.x; i < s.co_t * TC_K; i += blockDim.x) {
     const int o = i / TC_K, k = i - o * TC_K;
-    const int cl = k / KT, t = k - cl * KT;
+    const int t = tg, cw = cbi * TC_CB + k;                    // tap, channel within the group
     float v = 0.f;
     const int oc = cot * s.co_t + o;
-    if (oc < s.Cout && cl < ck && cl < TC_CK) v = w[((size_t)oc * s.Cin + c0 + cl) * KT + t];
+    if (oc < s.Cout && cw < cpg && t < KT) v = w[((size_t)oc * s.Cin + g * cpg + cw) * KT + t];
     const float h = tf32_hi(v);
     *reinterpret_cast<float *>(hi + tc_tile_off(o, k)) = h;
     *reinterpret_cast<float *>(lo + tc_tile_off(o, k)) = v - h;
   }
 }
 
+// x [B][Cin][HW] -> xt [B][HW][dg * cbs_pg][32]; channel ch of group g sits in block g*cbs_pg + (ch - g*cpg)/32,
+// slot (ch - g*cpg) % 32 (identity when Cin/dg is a multiple of 32; pad slots are zero-filled by the caller).
+// grid (pixel blocks of 32, channel blocks of 64, B), 256 threads.
+__global__ void __launch_bounds__(256) k_dcn_nhwc(const float *__restrict__ x, float *__restrict__ xt,
+                                                  const DcnShapeTc s) {
+  __shared__ float tile[64][33];
+  const long long HW = (long long)s.H * s.W;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64, b = blockIdx.z;
+  const int Cp = s.dg * s.cbs_pg * TC_CB;
+  const int cpg = s.Cin / s.dg;
+  {
+    const int px = threadIdx.x & 31, cr = threadIdx.x >> 5;
+    for (int c = cr; c < 64; c += 8) {
+      float v = 0.f;
+      if (c0 + c < s.Cin && p0 + px < HW) v = __ldg(x + ((long long)b * s.Cin + c0 + c) * HW + p0 + px);
+      tile[c][px] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int c = threadIdx.x & 63, pr = threadIdx.x >> 6;
+    const int ch = c0 + c;
+    if (ch < s.Cin) {
+      const int g = ch / cpg, within = ch - g * cpg;
+      const int slot = (g * s.cbs_pg + within / TC_CB) * TC_CB + within % TC_CB;
+      for (int px = pr; px < 32; px += 4)
+        if (p0 + px < HW) xt[((long long)b * HW + p0 + px) * Cp + slot] = tile[c][px];
+    }
+  }
+}
+
+// cycle breakdown of CTA (0,0), thread 0 (tools/dbg_dcn_stats.py): total, meta, wait-mma, sample+sync, wait-B, issue, epilogue
+__device__ long long g_dcn_dbg[8];
+
 template <int CO_T>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_dcn_forward_tc(const float *__restrict__ x, const float *__restrict__ offset, const float *__restrict__ mask,
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset, const float *__restrict__ mask,
                  const float *__restrict__ wtiles, const float *__restrict__ bias, float *__restrict__ y,
                  const DcnShapeTc s) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
@@ -100,8 +145,7 @@ k_dcn_forward_tc(const float *__restrict__ x, const float *__restrict__ offset, 
   const int b = blockIdx.x / tiles;
   const long long p_base = (long long)(blockIdx.x - b * tiles) * TC_TP;
   const int cot = blockIdx.y;
-  const int cpg = s.Cin / s.dg;
-  const int chunks_pg = (cpg + TC_CK - 1) / TC_CK;
+  const int Cp = s.dg * s.cbs_pg * TC_CB;       // channel pitch of the channels-last copy
 
   if (tid == 0) {
     mbar_init(&bar_b, 1);
@@ -119,18 +163,28 @@ k_dcn_forward_tc(const float *__restrict__ x, const float *__restrict__ offset, 
   const uint32_t tm = tmem_base;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO_T >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
 
+  const bool dbg = (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0);
+  long long d_meta = 0, d_wmma = 0, d_samp = 0, d_wb = 0, d_issue = 0, d_epi = 0, tq;
+  const long long d_start = clock64();
+  // sampler geometry: a warp gather covers 4 pixels x 32 channels (lane = quad * 4 + pixel): four fully used
+  // 128-byte lines per instruction -- the L1 data pipe moves a line per wavefront, so this is what makes the
+  // 36x re-read of the input (9 taps x 4 corners) affordable; the 16-byte stores into the UMMA tile are 2-way
+  // bank conflicted in exchange (k-chunks of one pixel are 128 bytes apart)
+  const int sp = lane & 3, sq = lane >> 2;
+  const float *xbat = xt + (long long)b * HW * Cp + sq * 4;
   int chunk = 0;
   for (int g = 0; g < s.dg; ++g) {
+    tq = clock64();
     // ---- bilinear geometry of every (tap, pixel) of this deformable group (mask folded into the weights)
     if (chunk > 0) mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));   // (meta is not read by the MMAs, but keep the order simple)
     __syncthreads();
-    for (int idx = tid; idx < KT * TC_TP; idx += TC_THREADS) {
+    for (int idx = tid; idx < 9 * TC_TP; idx += TC_THREADS) {
       const int t = idx / TC_TP, pp = idx - t * TC_TP;
       const long long p = p_base + pp;
       TapMetaTc mt;
 #pragma unroll
       for (int q = 0; q < 4; ++q) { mt.o[q] = 0; mt.w[q] = 0.f; }
-      if (p < HWo) {
+      if (p < HWo && t < KT) {
         const int ho = (int)(p / s.Wo), wo = (int)(p - (long long)ho * s.Wo);
         const int i = t / s.kw, j = t - i * s.kw;
         const float *op = offset + ((long long)b * s.dg + g) * 2 * KT * HWo;
@@ -152,84 +206,80 @@ k_dcn_forward_tc(const float *__restrict__ x, const float *__restrict__ offset, 
       meta[idx] = mt;
     }
     __syncthreads();
-    for (int cc = 0; cc < chunks_pg; ++cc, ++chunk) {
-      const int c0 = g * cpg + cc * TC_CK;
-      const int ck = min(TC_CK, (g + 1) * cpg - c0);
-      // the previous chunk's MMAs must have consumed A and B before they are overwritten
-      if (chunk > 0) mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));
-      if (tid == 0) {  // B operand (hi + lo tiles, contiguous in the workspace): two TMA bulk copies
-        const float *src = wtiles + ((size_t)cot * s.n_chunks + chunk) * 2 * (size_t)CO_T * TC_K;
-        mbar_expect_tx(&bar_b, 2u * B_BYTES);
-        for (uint32_t off = 0; off < 2u * B_BYTES; off += 18432u)
-          bulk_g2s(b_hi + off, reinterpret_cast<const unsigned char *>(src) + off, 18432u, &bar_b);
-      }
-      // ---- A operand: sampled column tile, split into TF32 hi / lo, written in the UMMA layout.
-      //      work item = (pixel, tap, half of the chunk's channels): the (tap, pixel) geometry is read
-      //      once and reused for 4 channels (16 independent gathers in flight per item)
-      for (int idx = tid; idx < TC_TP * KT * 2; idx += TC_THREADS) {
-        const int pp = idx & (TC_TP - 1), r = idx >> 7;       // r = t * 2 + half
-        const int t = r >> 1, half = r & 1;
-        const TapMetaTc mt = meta[t * TC_TP + pp];
-        const float *xp = x + ((long long)b * s.Cin + c0 + half * 4) * HW;
-        float v[4];
+    d_meta += clock64() - tq;
+    for (int tg = 0; tg < TC_NTG; ++tg) {     // one tap per chunk
+      for (int cbi = 0; cbi < s.cbs_pg; ++cbi, ++chunk) {
+        tq = clock64();
+        // the previous chunk's MMAs must have consumed A and B before they are overwritten
+        if (chunk > 0) mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));
+        d_wmma += clock64() - tq;
+        tq = clock64();
+        if (tid == 0) {  // B operand (hi + lo tiles, contiguous in the workspace): TMA bulk copies
+          const float *src = wtiles + ((size_t)cot * s.n_chunks + chunk) * 2 * (size_t)CO_T * TC_K;
+          mbar_expect_tx(&bar_b, 2u * B_BYTES);
+          for (uint32_t off = 0; off < 2u * B_BYTES; off += 8192u)
+            bulk_g2s(b_hi + off, reinterpret_cast<const unsigned char *>(src) + off, 8192u, &bar_b);
+        }
+        // ---- A operand: sampled column tile of 32 channels of one tap, split into TF32 hi / lo, UMMA layout.
+        //      warp item = 4 pixels: every lane gathers the 4 corners of its pixel as 16-byte pieces
+        //      (4 channels) of the channels-last copy
+        const float *xb = xbat + (long long)(g * s.cbs_pg + cbi) * TC_CB;
+#pragma unroll 2
+        for (int wi = warp; wi < TC_TP / 4; wi += TC_THREADS / 32) {
+          const int pp = wi * 4 + sp;
+          const TapMetaTc mt = meta[tg * TC_TP + pp];
+          float4 u[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float val = 0.f;
-          if (half * 4 + q < ck) {
-            const float *xc = xp + (long long)q * HW;
-            val = mt.w[0] * __ldg(xc + mt.o[0]);
-            val = fmaf(mt.w[1], __ldg(xc + mt.o[1]), val);
-            val = fmaf(mt.w[2], __ldg(xc + mt.o[2]), val);
-            val = fmaf(mt.w[3], __ldg(xc + mt.o[3]), val);
-          }
-          v[q] = val;
+          for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)mt.o[q] * Cp));
+          float4 v;
+          v.x = fmaf(mt.w[3], u[3].x, fmaf(mt.w[2], u[2].x, fmaf(mt.w[1], u[1].x, mt.w[0] * u[0].x)));
+          v.y = fmaf(mt.w[3], u[3].y, fmaf(mt.w[2], u[2].y, fmaf(mt.w[1], u[1].y, mt.w[0] * u[0].y)));
+          v.z = fmaf(mt.w[3], u[3].z, fmaf(mt.w[2], u[2].z, fmaf(mt.w[1], u[1].z, mt.w[0] * u[0].z)));
+          v.w = fmaf(mt.w[3], u[3].w, fmaf(mt.w[2], u[2].w, fmaf(mt.w[1], u[1].w, mt.w[0] * u[0].w)));
+          const float4 h4 = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+          const uint32_t off = tc_tile_off(pp, sq * 4);
+          *reinterpret_cast<float4 *>(a_hi + off) = h4;
+          *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h4.x, v.y - h4.y, v.z - h4.z, v.w - h4.w);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = (half * 4 + q) * KT + t;
-          const float h = tf32_hi(v[q]);
-          const uint32_t off = tc_tile_off(pp, k);
-          *reinterpret_cast<float *>(a_hi + off) = h;
-          *reinterpret_cast<float *>(a_lo + off) = v[q] - h;
-        }
-      }
-      // K rows beyond 8 * KT (kernels smaller than 3x3) stay zero
-      if (KT < 9)
-        for (int idx = tid; idx < TC_TP * (TC_K - 8 * KT); idx += TC_THREADS) {
-          const int pp = idx & (TC_TP - 1), k = 8 * KT + (idx >> 7);
-          *reinterpret_cast<float *>(a_hi + tc_tile_off(pp, k)) = 0.f;
-          *reinterpret_cast<float *>(a_lo + tc_tile_off(pp, k)) = 0.f;
-        }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(&bar_b, (uint32_t)(chunk & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        d_samp += clock64() - tq;
+        if (tid == 0) {
+          tq = clock64();
+          mbar_wait(&bar_b, (uint32_t)(chunk & 1));
+          d_wb += clock64() - tq;
+          tq = clock64();
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
 #pragma unroll 1
-        for (int ks = 0; ks < TC_K / 8; ++ks) {   // one UMMA per 8 k (two 16-byte k-chunks), 3 per step (3xTF32)
-          const uint32_t koff = (uint32_t)ks * 2u * TC_LBO;
-          const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
-          const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
-          const uint32_t acc0 = (chunk > 0 || ks > 0) ? 1u : 0u;
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dal), "l"(dbh),
-                       "r"(idesc), "r"(acc0) : "memory");      // lo * hi   (small terms first)
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbl),
-                       "r"(idesc), "r"(1u) : "memory");        // hi * lo
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbh),
-                       "r"(idesc), "r"(1u) : "memory");        // hi * hi
+          for (int ks = 0; ks < TC_K / 8; ++ks) {   // one UMMA per 8 k (two 16-byte k-chunks), 3 per step (3xTF32)
+            const uint32_t koff = (uint32_t)ks * 2u * TC_LBO;
+            const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
+            const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
+            const uint32_t acc0 = (chunk > 0 || ks > 0) ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dal), "l"(dbh),
+                         "r"(idesc), "r"(acc0) : "memory");      // lo * hi   (small terms first)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbl),
+                         "r"(idesc), "r"(1u) : "memory");        // hi * lo
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbh),
+                         "r"(idesc), "r"(1u) : "memory");        // hi * hi
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&bar_mma)) : "memory");
+          d_issue += clock64() - tq;
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(&bar_mma)) : "memory");
       }
     }
   }
   // ---- epilogue: TMEM -> registers -> bias -> global (coalesced along pixels)
+  tq = clock64();
   mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));
+  d_wmma += clock64() - tq;
+  tq = clock64();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (warp < 8) {
     constexpr int HALF = CO_T / 2;                 // columns per warp group (warps 0-3: first half, 4-7: second)
@@ -263,7 +313,12 @@ k_dcn_forward_tc(const float *__restrict__ x, const float *__restrict__ offset, 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  d_epi = clock64() - tq;
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(CO_T));
+  if (dbg) {
+    g_dcn_dbg[0] = clock64() - d_start; g_dcn_dbg[1] = d_meta; g_dcn_dbg[2] = d_wmma; g_dcn_dbg[3] = d_samp;
+    g_dcn_dbg[4] = d_wb; g_dcn_dbg[5] = d_issue; g_dcn_dbg[6] = d_epi; g_dcn_dbg[7] = chunk;
+  }
 }
 
 static void fill_shape(DcnShapeTc *s, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph,
@@ -274,18 +329,24 @@ static void fill_shape(DcnShapeTc *s, int b, int cin, int h, int w, int cout, in
   s->Wo = (w + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
   s->co_t = cout > 64 ? 128 : 64;
   const int cpg = cin / dg;
-  s->n_chunks = dg * ((cpg + TC_CK - 1) / TC_CK);
+  s->cbs_pg = (cpg + TC_CB - 1) / TC_CB;
+  s->n_chunks = dg * TC_NTG * s->cbs_pg;
 }
 
-size_t dcn_tc_workspace_bytes(int cin, int cout, int dg) {
+static size_t tc_weight_bytes(const DcnShapeTc &s) {
+  const int cot = (s.Cout + s.co_t - 1) / s.co_t;
+  return align_up((size_t)cot * s.n_chunks * 2 * s.co_t * TC_K * 4, 256);
+}
+
+// weights re-tiled (hi/lo) + the channels-last copy of the input
+size_t dcn_tc_workspace_bytes(int b, int cin, int h, int w, int cout, int dg) {
   DcnShapeTc s;
-  fill_shape(&s, 1, cin, 8, 8, cout, 3, 3, 1, 1, 1, 1, 1, 1, dg);
-  const int cot = (cout + s.co_t - 1) / s.co_t;
-  return (size_t)cot * s.n_chunks * 2 * s.co_t * TC_K * 4;
+  fill_shape(&s, b, cin, h, w, cout, 3, 3, 1, 1, 1, 1, 1, 1, dg);
+  return tc_weight_bytes(s) + align_up((size_t)b * h * w * dg * s.cbs_pg * TC_CB * 4, 256);
 }
 
 // Tensor-core forward.  Requires kh*kw <= 9 (checked by the caller) and a workspace of
-// dcn_tc_workspace_bytes(); enqueues the weight re-tiling kernel + the fused forward.
+// dcn_tc_workspace_bytes(); enqueues the weight re-tiling, the channels-last copy and the fused forward.
 int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
                    const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
                    int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream) {
@@ -293,22 +354,34 @@ int dcn_forward_tc(const float *input, const float *offset, const float *mask, c
   fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
   const int cot = (cout + s.co_t - 1) / s.co_t;
   float *ws = reinterpret_cast<float *>(workspace);
+  float *xt = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + tc_weight_bytes(s));
   k_dcn_prep_weights<<<cot * s.n_chunks, 256, 0, stream>>>(weight, s, ws);
   CNB_CHECK_LAUNCH("cnb_dcnv2_forward weight tiles");
+  const long long HW = (long long)h * w;
+  if ((cin / dg) % TC_CB != 0)   // pad slots of the last channel block of every group must read as zero
+    CNB_CUDA(cudaMemsetAsync(xt, 0, (size_t)b * HW * dg * s.cbs_pg * TC_CB * 4, stream));
+  dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((cin + 63) / 64), (unsigned)b);
+  k_dcn_nhwc<<<tgrid, 256, 0, stream>>>(input, xt, s);
+  CNB_CHECK_LAUNCH("cnb_dcnv2_forward channels-last copy");
   const long long HWo = (long long)s.Ho * s.Wo;
   const int tiles = (int)((HWo + TC_TP - 1) / TC_TP);
   dim3 grid((unsigned)(b * tiles), (unsigned)cot);
   const size_t smem = 2 * (size_t)TC_A_BYTES + 2 * (size_t)s.co_t * TC_K * 4 + sizeof(TapMetaTc) * 9 * TC_TP;
   if (s.co_t == 64) {
     CNB_CUDA(cudaFuncSetAttribute(k_dcn_forward_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dcn_forward_tc<64><<<grid, TC_THREADS, smem, stream>>>(input, offset, mask, ws, bias, output, s);
+    k_dcn_forward_tc<64><<<grid, TC_THREADS, smem, stream>>>(xt, offset, mask, ws, bias, output, s);
   } else {
     CNB_CUDA(cudaFuncSetAttribute(k_dcn_forward_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dcn_forward_tc<128><<<grid, TC_THREADS, smem, stream>>>(input, offset, mask, ws, bias, output, s);
+    k_dcn_forward_tc<128><<<grid, TC_THREADS, smem, stream>>>(xt, offset, mask, ws, bias, output, s);
   }
   CNB_CHECK_LAUNCH("cnb_dcnv2_forward (tcgen05)");
-  count_launch(2);
+  count_launch(3);
   return CNB_OK;
 }
 
 }  // namespace cnb
+
+// debug: cycle breakdown of the last tensor-core forward (CTA 0, thread 0); synchronises the device
+extern "C" int cnb_debug_dcn_stats(long long *out8) {
+  return cudaMemcpyFromSymbol(out8, cnb::g_dcn_dbg, sizeof(long long) * 8) == cudaSuccess ? 0 : 1;
+}
