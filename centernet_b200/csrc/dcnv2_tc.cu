@@ -224,13 +224,16 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
         //      warp item = 4 pixels: every lane gathers the 4 corners of its pixel as 16-byte pieces
         //      (4 channels) of the channels-last copy
         const float *xb = xbat + (long long)(g * s.cbs_pg + cbi) * TC_CB;
-#pragma unroll 2
-        for (int wi = warp; wi < TC_TP / 4; wi += TC_THREADS / 32) {
-          const int pp = wi * 4 + sp;
-          const TapMetaTc mt = meta[tg * TC_TP + pp];
-          float4 u[4];
+        //      both of a warp's items are gathered before either is reduced: 8 independent 16-byte loads in flight
+        static_assert(TC_TP / 4 == 2 * (TC_THREADS / 32), "two warp items per warp and chunk");
+        const int pp0 = warp * 4 + sp, pp1 = pp0 + TC_TP / 2;
+        const TapMetaTc m0 = meta[tg * TC_TP + pp0], m1 = meta[tg * TC_TP + pp1];
+        float4 u0[4], u1[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)mt.o[q] * Cp));
+        for (int q = 0; q < 4; ++q) u0[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m0.o[q] * Cp));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u1[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m1.o[q] * Cp));
+        auto reduce_store = [&](const TapMetaTc &mt, const float4 (&u)[4], int pp) {
           float4 v;
           v.x = fmaf(mt.w[3], u[3].x, fmaf(mt.w[2], u[2].x, fmaf(mt.w[1], u[1].x, mt.w[0] * u[0].x)));
           v.y = fmaf(mt.w[3], u[3].y, fmaf(mt.w[2], u[2].y, fmaf(mt.w[1], u[1].y, mt.w[0] * u[0].y)));
@@ -240,7 +243,9 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
           const uint32_t off = tc_tile_off(pp, sq * 4);
           *reinterpret_cast<float4 *>(a_hi + off) = h4;
           *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h4.x, v.y - h4.y, v.z - h4.z, v.w - h4.w);
-        }
+        };
+        reduce_store(m0, u0, pp0);
+        reduce_store(m1, u1, pp1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
