@@ -166,11 +166,13 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
   const bool dbg = (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0);
   long long d_meta = 0, d_wmma = 0, d_samp = 0, d_wb = 0, d_issue = 0, d_epi = 0, tq;
   const long long d_start = clock64();
-  // sampler geometry: a warp gather covers 4 pixels x 32 channels (lane = quad * 4 + pixel): four fully used
-  // 128-byte lines per instruction -- the L1 data pipe moves a line per wavefront, so this is what makes the
-  // 36x re-read of the input (9 taps x 4 corners) affordable; the 16-byte stores into the UMMA tile are 2-way
-  // bank conflicted in exchange (k-chunks of one pixel are 128 bytes apart)
-  const int sp = lane & 3, sq = lane >> 2;
+  // sampler geometry: a warp gather covers 4 pixels x 32 channels with lane = pixel * 8 + quad, so each
+  // quarter-warp (the unit the L1 data pipe serves for 16-byte accesses) reads ONE fully used 128-byte
+  // line: 4 wavefronts per gather instead of one per 32-byte sector.  This is what makes the 36x re-read
+  // of the input (9 taps x 4 corners) affordable.  The UMMA tile wants the opposite lane order (a
+  // quarter-warp = 8 rows of one k-chunk, 128 contiguous bytes), so the reduced values are transposed
+  // across the warp with shuffles before the conflict-free 16-byte stores.
+  const int sp = lane >> 3, sq = lane & 7;
   const float *xbat = xt + (long long)b * HW * Cp + sq * 4;
   int chunk = 0;
   for (int g = 0; g < s.dg; ++g) {
@@ -224,28 +226,43 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
         //      warp item = 4 pixels: every lane gathers the 4 corners of its pixel as 16-byte pieces
         //      (4 channels) of the channels-last copy
         const float *xb = xbat + (long long)(g * s.cbs_pg + cbi) * TC_CB;
-        //      both of a warp's items are gathered before either is reduced: 8 independent 16-byte loads in flight
+        //      both of a warp's items (pixels 8w..8w+3 and 8w+4..8w+7) are gathered before either is reduced
         static_assert(TC_TP / 4 == 2 * (TC_THREADS / 32), "two warp items per warp and chunk");
-        const int pp0 = warp * 4 + sp, pp1 = pp0 + TC_TP / 2;
+        const int pp0 = warp * 8 + sp, pp1 = pp0 + 4;
         const TapMetaTc m0 = meta[tg * TC_TP + pp0], m1 = meta[tg * TC_TP + pp1];
         float4 u0[4], u1[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) u0[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m0.o[q] * Cp));
 #pragma unroll
         for (int q = 0; q < 4; ++q) u1[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m1.o[q] * Cp));
-        auto reduce_store = [&](const TapMetaTc &mt, const float4 (&u)[4], int pp) {
+        auto reduce = [&](const TapMetaTc &mt, const float4 (&u)[4]) {
           float4 v;
           v.x = fmaf(mt.w[3], u[3].x, fmaf(mt.w[2], u[2].x, fmaf(mt.w[1], u[1].x, mt.w[0] * u[0].x)));
           v.y = fmaf(mt.w[3], u[3].y, fmaf(mt.w[2], u[2].y, fmaf(mt.w[1], u[1].y, mt.w[0] * u[0].y)));
           v.z = fmaf(mt.w[3], u[3].z, fmaf(mt.w[2], u[2].z, fmaf(mt.w[1], u[1].z, mt.w[0] * u[0].z)));
           v.w = fmaf(mt.w[3], u[3].w, fmaf(mt.w[2], u[2].w, fmaf(mt.w[1], u[1].w, mt.w[0] * u[0].w)));
+          return v;
+        };
+        const float4 v0 = reduce(m0, u0), v1 = reduce(m1, u1);   // (row sp, quad sq) and (row 4 + sp, quad sq)
+        // transpose: store instruction j writes (row = lane & 7, quad = (lane >> 3) + 4 j); that value lives in
+        // lane (row & 3) * 8 + quad, in v0 for rows 0-3 and v1 for rows 4-7
+        const int row = lane & 7;
+        const bool upper = row >= 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int quad = (lane >> 3) + 4 * j;
+          const int src = (row & 3) * 8 + quad;
+          float4 a, c;
+          a.x = __shfl_sync(0xffffffffu, v0.x, src); c.x = __shfl_sync(0xffffffffu, v1.x, src);
+          a.y = __shfl_sync(0xffffffffu, v0.y, src); c.y = __shfl_sync(0xffffffffu, v1.y, src);
+          a.z = __shfl_sync(0xffffffffu, v0.z, src); c.z = __shfl_sync(0xffffffffu, v1.z, src);
+          a.w = __shfl_sync(0xffffffffu, v0.w, src); c.w = __shfl_sync(0xffffffffu, v1.w, src);
+          const float4 v = upper ? c : a;
           const float4 h4 = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-          const uint32_t off = tc_tile_off(pp, sq * 4);
+          const uint32_t off = tc_tile_off(warp * 8 + row, quad * 4);
           *reinterpret_cast<float4 *>(a_hi + off) = h4;
           *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h4.x, v.y - h4.y, v.z - h4.z, v.w - h4.w);
-        };
-        reduce_store(m0, u0, pp0);
-        reduce_store(m1, u1, pp1);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
