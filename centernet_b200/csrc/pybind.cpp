@@ -74,6 +74,23 @@ PYBIND11_MODULE(_C, m) {
   m.def("sigmoid", [](P x, P out, long long n, P stream) {
     check(cnb_sigmoid(ptr<const float>(x), ptr<float>(out), n, ptr<void>(stream)), "cnb_sigmoid");
   });
+  m.def("psroi_pooling_forward", [](P data, P rois, P trans, P out, P cnt, int b, int c, int h, int w, int n, int ct,
+                                    int no_trans, float scale, int od, int gs, int ps, int part, int spp, float tstd,
+                                    P stream) {
+    check(cnb_psroi_pooling_forward(ptr<const float>(data), ptr<const float>(rois), ptr<const float>(trans),
+                                    ptr<float>(out), ptr<float>(cnt), b, c, h, w, n, ct, no_trans, scale, od, gs, ps,
+                                    part, spp, tstd, ptr<void>(stream)),
+          "cnb_psroi_pooling_forward");
+  });
+  m.def("psroi_pooling_backward", [](P gout, P data, P rois, P trans, P cnt, P gdata, P gtrans, int b, int c, int h,
+                                     int w, int n, int ct, int no_trans, float scale, int od, int gs, int ps, int part,
+                                     int spp, float tstd, P stream) {
+    check(cnb_psroi_pooling_backward(ptr<const float>(gout), ptr<const float>(data), ptr<const float>(rois),
+                                     ptr<const float>(trans), ptr<const float>(cnt), ptr<float>(gdata),
+                                     ptr<float>(gtrans), b, c, h, w, n, ct, no_trans, scale, od, gs, ps, part, spp,
+                                     tstd, ptr<void>(stream)),
+          "cnb_psroi_pooling_backward");
+  });
   m.def("ddd_decode", [](P heat, P rot, P depth, P dim, P wh, P reg, int b, int c, int h, int w, int k, P dets, P ws,
                          size_t wsb, P stream) {
     check(cnb_ddd_decode(ptr<const float>(heat), ptr<const float>(rot), ptr<const float>(depth),

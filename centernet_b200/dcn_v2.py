@@ -64,7 +64,7 @@ class DCN(DCNv2):
 
 
 class DCNv2Pooling(nn.Module):
-    """dcn_v2.py:73-106 (surface only; see DCNv2PoolingFunction)."""
+    """dcn_v2.py:73-106."""
 
     def __init__(self, spatial_scale, pooled_size, output_dim, no_trans, group_size=1, part_size=None,
                  sample_per_part=4, trans_std=.0):
@@ -83,13 +83,35 @@ class DCNv2Pooling(nn.Module):
 
 
 class DCNPooling(DCNv2Pooling):
-    """dcn_v2.py:108-171 (surface only)."""
+    """dcn_v2.py:108-171: the offsets and the modulation mask are predicted from a first, undeformed pooling
+    pass (`offset_fc`, `mask_fc`, last layers zero-initialised; same submodule names for state dicts)."""
 
     def __init__(self, spatial_scale, pooled_size, output_dim, no_trans, group_size=1, part_size=None,
                  sample_per_part=4, trans_std=.0, deform_fc_dim=1024):
         super().__init__(spatial_scale, pooled_size, output_dim, no_trans, group_size, part_size, sample_per_part,
                          trans_std)
         self.deform_fc_dim = deform_fc_dim
+        if not no_trans:
+            self.func_offset = DCNv2PoolingFunction(spatial_scale, pooled_size, output_dim, True, group_size,
+                                                    self.part_size, sample_per_part, trans_std)
+            feat = pooled_size * pooled_size * output_dim
+            self.offset_fc = nn.Sequential(
+                nn.Linear(feat, deform_fc_dim), nn.ReLU(inplace=True),
+                nn.Linear(deform_fc_dim, deform_fc_dim), nn.ReLU(inplace=True),
+                nn.Linear(deform_fc_dim, pooled_size * pooled_size * 2))
+            self.offset_fc[4].weight.data.zero_()
+            self.offset_fc[4].bias.data.zero_()
+            self.mask_fc = nn.Sequential(
+                nn.Linear(feat, deform_fc_dim), nn.ReLU(inplace=True),
+                nn.Linear(deform_fc_dim, pooled_size * pooled_size * 1), nn.Sigmoid())
+            self.mask_fc[2].weight.data.zero_()
+            self.mask_fc[2].bias.data.zero_()
 
     def forward(self, data, rois):
-        raise NotImplementedError("DCNPooling: deformable PSROI pooling is not implemented in centernet_b200")
+        if self.no_trans:
+            return self.func(data, rois, data.new())
+        n = rois.shape[0]
+        x = self.func_offset(data, rois, data.new())
+        offset = self.offset_fc(x.view(n, -1)).view(n, 2, self.pooled_size, self.pooled_size)
+        mask = self.mask_fc(x.view(n, -1)).view(n, 1, self.pooled_size, self.pooled_size)
+        return self.func(data, rois, offset) * mask

@@ -86,12 +86,69 @@ class DCNv2Function(object):
     forward = __call__
 
 
+class _PSROIPooling(Function):
+    """dcn_v2_func.py:76-146 as a modern autograd.Function."""
+
+    @staticmethod
+    def forward(ctx, data, rois, offset, spatial_scale, pooled_size, output_dim, no_trans, group_size, part_size,
+                sample_per_part, trans_std):
+        if not data.is_cuda:
+            raise NotImplementedError("DCNv2PoolingFunction: CUDA tensors only (dcn_v2_func.py:100-101)")
+        data, rois = f32c(data), f32c(rois)
+        if rois.dim() != 2 or rois.shape[1] != 5:
+            raise RuntimeError("DCNv2PoolingFunction: rois must be [n, 5], got %s" % (tuple(rois.shape),))
+        no_trans = bool(no_trans)
+        if not no_trans:
+            offset = f32c(offset)
+            if offset.dim() != 4 or offset.shape[0] < rois.shape[0] or tuple(offset.shape[2:]) != (part_size, part_size):
+                raise RuntimeError("DCNv2PoolingFunction: offset must be [>=n, 2*classes, %d, %d], got %s"
+                                   % (part_size, part_size, tuple(offset.shape)))
+        n, (b, c, h, w) = int(rois.shape[0]), data.shape
+        out = torch.empty((n, output_dim, pooled_size, pooled_size), dtype=torch.float32, device=data.device)
+        cnt = torch.empty_like(out)
+        ct = 2 if no_trans else int(offset.shape[1])
+        C.psroi_pooling_forward(ptr(data), ptr(rois), 0 if no_trans else ptr(offset), ptr(out), ptr(cnt), b, c, h, w,
+                                n, ct, int(no_trans), float(spatial_scale), output_dim, group_size, pooled_size,
+                                part_size, sample_per_part, float(trans_std), stream_ptr(data))
+        ctx.save_for_backward(data, rois, offset if not no_trans else data.new_empty(0), cnt)
+        ctx.cfg = (spatial_scale, pooled_size, output_dim, no_trans, group_size, part_size, sample_per_part, trans_std, ct)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError("DCNv2PoolingFunction: CUDA tensors only (dcn_v2_func.py:117-118)")
+        data, rois, offset, cnt = ctx.saved_tensors
+        spatial_scale, pooled_size, output_dim, no_trans, group_size, part_size, sample_per_part, trans_std, ct = ctx.cfg
+        grad_output = f32c(grad_output)
+        grad_input = torch.zeros_like(data)                                   # :119-120, accumulated into
+        grad_offset = None if no_trans else torch.zeros_like(offset)
+        n, (b, c, h, w) = int(rois.shape[0]), data.shape
+        C.psroi_pooling_backward(ptr(grad_output), ptr(data), ptr(rois), 0 if no_trans else ptr(offset), ptr(cnt),
+                                 ptr(grad_input), 0 if no_trans else ptr(grad_offset), b, c, h, w, n, ct, int(no_trans),
+                                 float(spatial_scale), output_dim, group_size, pooled_size, part_size, sample_per_part,
+                                 float(trans_std), stream_ptr(data))
+        return (grad_input, None, grad_offset) + (None,) * 8
+
+
 class DCNv2PoolingFunction(object):
-    """Deformable PSROI pooling (dcn_v2_func.py:76-146).  No CenterNet network instantiates it
-    (SURVEY.md section 2b); it is a "next" row (section 8f N4) and not implemented yet."""
+    """Deformable PSROI pooling, callable as an instance like the reference's old-style Function
+    (dcn_v2_func.py:76-146): `DCNv2PoolingFunction(spatial_scale, pooled_size, output_dim, no_trans,
+    group_size=1, part_size=None, sample_per_part=4, trans_std=.0)(data, rois, offset)`."""
 
-    def __init__(self, *args, **kwargs):
-        self.args = (args, kwargs)
+    def __init__(self, spatial_scale, pooled_size, output_dim, no_trans, group_size=1, part_size=None,
+                 sample_per_part=4, trans_std=.0):
+        self.spatial_scale = spatial_scale
+        self.pooled_size = pooled_size
+        self.output_dim = output_dim
+        self.no_trans = no_trans
+        self.group_size = group_size
+        self.part_size = pooled_size if part_size is None else part_size
+        self.sample_per_part = sample_per_part
+        self.trans_std = trans_std
+        assert 0.0 <= self.trans_std <= 1.0                                    # :97
 
-    def __call__(self, *a, **k):
-        raise NotImplementedError("DCNv2PoolingFunction: deformable PSROI pooling is not implemented in centernet_b200")
+    def __call__(self, data, rois, offset):
+        return _PSROIPooling.apply(data, rois, offset, self.spatial_scale, self.pooled_size, self.output_dim,
+                                   self.no_trans, self.group_size, self.part_size, self.sample_per_part,
+                                   self.trans_std)

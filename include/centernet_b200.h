@@ -203,6 +203,27 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
                        int dil_h, int dil_w, int deformable_groups,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------- N4: deformable PSROI pooling
+ * Replaces dcn_v2_psroi_pooling_cuda_forward / _backward (src/dcn_v2_cuda.h:35-55,
+ * src/cuda/dcn_v2_psroi_pooling_cuda.cu:47-255).  data [b,c,h,w]; rois [num_rois,5]
+ * = (batch index, x1, y1, x2, y2); trans [num_rois, channels_trans, part, part] or
+ * NULL when no_trans; out / top_count [num_rois, output_dim, pooled, pooled].
+ * Backward ACCUMULATES into grad_data / grad_trans, which must arrive zero-filled
+ * (dcn_v2_func.py:119-120). */
+int cnb_psroi_pooling_forward(const float *data, const float *rois, const float *trans,
+                              float *out, float *top_count,
+                              int b, int c, int h, int w, int num_rois, int channels_trans,
+                              int no_trans, float spatial_scale, int output_dim, int group_size,
+                              int pooled_size, int part_size, int sample_per_part, float trans_std,
+                              void *stream);
+int cnb_psroi_pooling_backward(const float *grad_out, const float *data, const float *rois,
+                               const float *trans, const float *top_count,
+                               float *grad_data, float *grad_trans,
+                               int b, int c, int h, int w, int num_rois, int channels_trans,
+                               int no_trans, float spatial_scale, int output_dim, int group_size,
+                               int pooled_size, int part_size, int sample_per_part, float trans_std,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif
