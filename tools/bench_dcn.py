@@ -39,6 +39,29 @@ def run(B, Cin, H, W, Cout, iters=20):
         err_tv = (out_fp - ref).abs().max().item()
     except Exception as e:
         err_tv = str(e)[:40]
+    # forward + backward through autograd (this library: tcgen05 forward + fp32 backward kernels)
+    try:
+        from centernet_b200.dcn_v2_func import DCNv2Function
+        from torchvision.ops import deform_conv2d
+        leaves = [t.clone().requires_grad_(True) for t in (x, off, msk, w, bias)]
+        fn = DCNv2Function(1, 1, 1, 1)
+        def ours():
+            for t in leaves: t.grad = None
+            fn(*leaves).sum().backward()
+        def tv():
+            for t in leaves: t.grad = None
+            deform_conv2d(leaves[0], leaves[1], leaves[3], leaves[4], padding=1, mask=leaves[2]).sum().backward()
+        for name, f in (('fwd+bwd_ours', ours), ('fwd+bwd_torchvision', tv)):
+            for _ in range(2): f()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5): f()
+            e1.record(); torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / 5
+    except Exception as e:
+        res['fwd+bwd_error'] = -1.0
+        print('fwd+bwd timing failed:', str(e)[:100])
     flops = 2.0 * Cout * Cin * 9 * H * W * B
     print('B=%d %d@%dx%d->%d: ' % (B, Cin, H, W, Cout) + ', '.join('%s %.3f ms (%.1f TFLOP/s)' % (k, v, flops / v / 1e9) for k, v in res.items()),
           '| max|tc-fp32| = %.2e, max|fp32-tv| = %s' % ((out_tc - out_fp).abs().max().item(), err_tv))
