@@ -246,7 +246,9 @@ __device__ __forceinline__ void build_bwd_meta(const DcnShape &s, const float *o
 __global__ void __launch_bounds__(DCN_THREADS, 1)
 k_dcn_bwd_data(const float *__restrict__ x, const float *__restrict__ offset, const float *__restrict__ mask,
                const float *__restrict__ weight, const float *__restrict__ gy, float *__restrict__ gx,
-               float *__restrict__ goff, float *__restrict__ gmask, const DcnShape s) {
+               float *__restrict__ goff, float *__restrict__ gmask, const DcnShape s, const int csplit) {
+  // csplit > 1 (small maps: too few pixel tiles to fill the GPU): blockIdx.y takes every csplit-th channel
+  // chunk and dOffset / dMask are accumulated with atomics into the zero-filled outputs
   extern __shared__ __align__(16) unsigned char dcn_smem[];
   const int KT = s.kh * s.kw;
   constexpr int KC = DCN_CK * DCN_KT_MAX;
@@ -271,6 +273,7 @@ k_dcn_bwd_data(const float *__restrict__ x, const float *__restrict__ offset, co
     build_bwd_meta(s, offset, mask, b, g, p_base, HWo, meta);
     for (int idx = tid; idx < KT * DCN_TP; idx += DCN_THREADS) { accm[idx] = 0.f; acch[idx] = 0.f; accw[idx] = 0.f; }
     for (int c0 = g * cpg; c0 < (g + 1) * cpg; c0 += DCN_CK) {
+      if (csplit > 1 && ((c0 - g * cpg) / DCN_CK) % csplit != (int)blockIdx.y) continue;   // CTA-uniform
       const int ck = min(DCN_CK, (g + 1) * cpg - c0);
       const int kc = ck * KT;
       float acc[9][4];
@@ -350,11 +353,14 @@ k_dcn_bwd_data(const float *__restrict__ x, const float *__restrict__ offset, co
       const int t = idx / DCN_TP, pp = idx - t * DCN_TP;
       const long long p = p_base + pp;
       if (p >= HWo) continue;
-      if (gmask) gmask[(((long long)b * s.dg + g) * KT + t) * HWo + p] = accm[idx];
-      if (goff) {
-        float *op = goff + ((long long)b * s.dg + g) * 2 * KT * HWo;
-        op[(2 * t) * HWo + p] = acch[idx];
-        op[(2 * t + 1) * HWo + p] = accw[idx];
+      float *mp = gmask ? gmask + (((long long)b * s.dg + g) * KT + t) * HWo + p : nullptr;
+      float *op = goff ? goff + ((long long)b * s.dg + g) * 2 * KT * HWo + p : nullptr;
+      if (csplit > 1) {
+        if (mp) atomicAdd(mp, accm[idx]);
+        if (op) { atomicAdd(op + (2 * t) * HWo, acch[idx]); atomicAdd(op + (2 * t + 1) * HWo, accw[idx]); }
+      } else {
+        if (mp) *mp = accm[idx];
+        if (op) { op[(2 * t) * HWo] = acch[idx]; op[(2 * t + 1) * HWo] = accw[idx]; }
       }
     }
   }
@@ -551,8 +557,14 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
                         sizeof(float) * 64 * DCN_TP + sizeof(float) * 64 * (KC + 1) +
                         3 * sizeof(float) * DCN_KT_MAX * DCN_TP;
     CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_data, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dcn_bwd_data<<<(unsigned)(b * tiles), DCN_THREADS, smem, stream>>>(input, offset, mask, weight, grad_output,
-                                                                         grad_input, grad_offset, grad_mask, s);
+    // small maps: fewer pixel tiles than SMs -> also split the channel chunks over blockIdx.y
+    const int chunks_pg = (cin / deformable_groups + DCN_CK - 1) / DCN_CK;
+    int csplit = (int)((2ll * num_sms() + (long long)b * tiles - 1) / ((long long)b * tiles));
+    if (csplit > chunks_pg) csplit = chunks_pg;
+    if (csplit < 1 || (long long)b * tiles >= num_sms()) csplit = 1;
+    dim3 dgrid((unsigned)(b * tiles), (unsigned)csplit);
+    k_dcn_bwd_data<<<dgrid, DCN_THREADS, smem, stream>>>(input, offset, mask, weight, grad_output, grad_input,
+                                                         grad_offset, grad_mask, s, csplit);
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward data");
     ++launches;
   }
