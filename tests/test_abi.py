@@ -52,3 +52,28 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "oracle/" not in txt and "oracle." not in txt, f
+
+
+def test_validation_of_later_entry_points():
+    """Argument checks of the logits decode, DCNv2 workspace, PSROI pooling and edge aggregation run before any
+    CUDA call, so they can be exercised without a GPU."""
+    from centernet_b200 import _C
+    # fused-sigmoid decode: same workspace as the heat-map path in the hot geometry (no heat map is materialised),
+    # plus one map for other geometries
+    hot = _C.ctdet_logits_workspace_bytes(0, 64, 80, 128, 128, 100)
+    assert 0 < hot <= _C.topk_workspace_bytes(64, 80, 128, 128, 100)
+    generic = _C.ctdet_logits_workspace_bytes(0, 2, 5, 40, 60, 33)
+    assert generic >= 2 * 5 * 40 * 60 * 4
+    with pytest.raises(RuntimeError, match="null pointer"):
+        _C.ctdet_decode_logits(0, 0, 0, 0, 1, 80, 128, 128, 100, 0, 0, 0, 0)
+    # DCNv2 tensor-core forward: re-tiled weights (hi + lo, 18 chunks of [64][32]) + channels-last copy of the input
+    ws = _C.dcnv2_workspace_bytes(16, 64, 64, 128, 128, 3, 3, 1, 1, 1, 1)
+    assert ws == 18 * 2 * 64 * 32 * 4 + 16 * 128 * 128 * 64 * 4
+    assert _C.dcnv2_workspace_bytes(16, 64, 64, 128, 128, 5, 5, 1, 2, 1, 1) == 0      # 25 taps: fp32 path only
+    # PSROI pooling: position-sensitive channels must exist
+    with pytest.raises(RuntimeError, match="channels"):
+        _C.psroi_pooling_forward(16, 16, 0, 16, 16, 1, 8, 9, 9, 2, 2, 1, 0.25, 4, 2, 3, 3, 2, 0.0, 0)
+    with pytest.raises(RuntimeError, match="offsets"):
+        _C.psroi_pooling_forward(16, 16, 0, 16, 16, 1, 8, 9, 9, 2, 3, 0, 0.25, 2, 2, 3, 3, 2, 0.0, 0)
+    with pytest.raises(RuntimeError, match="in-place"):
+        _C.edge_aggregate(16, 16, 1, 1, 8, 8, 0.1, 1, 0)
