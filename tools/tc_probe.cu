@@ -8,7 +8,8 @@
 #include <vector>
 #include <cuda_runtime.h>
 
-constexpr int M = 128, N = 64, K = 72;           // one DCN chunk: 8 channels x 9 taps
+constexpr int M = 128, N = 64, K = 72;           // first chunk shape of the DCN kernel (8 channels x 9 taps); production now uses
+                                                 // K = 32 per chunk with the same descriptor fields (LBO 128 B, SBO = K/4 * 128 B)
 constexpr int KC = K / 4;                        // 16-byte k-chunks (4 tf32 each)
 constexpr uint32_t LBO = 128;                    // bytes between consecutive k-chunks (one 8x16B core matrix)
 constexpr uint32_t SBO_A = KC * 128;             // bytes between 8-row groups
