@@ -110,3 +110,15 @@ def test_splat():
     # SURVEY appendix A facts
     assert int(image_np.gaussian_radius((10, 20))) == 3 and int(image_np.gaussian_radius((1, 1))) == 0
     assert image_np.gaussian2d(7, 7 / 6)[3, 3] == 1.0
+
+
+def test_timed_cpu_port_reproduces_the_reference():
+    """oracle/torch_port.py is what bench.py times as the reference's CPU path; it must give the reference's numbers
+    (tools/compare_port_with_reference.py checks it against the live reference in the build container)."""
+    import torch
+    from oracle import torch_port
+    g = golden("ctdet_noise")
+    K = int(g["K"])
+    heat, wh, reg = (torch.from_numpy(g[k]) for k in ("heat", "wh", "reg"))
+    np.testing.assert_array_equal(torch_port.ctdet_decode(heat.clone(), wh, reg=reg, K=K).numpy(), g["dets"])
+    np.testing.assert_array_equal(torch_port.ctdet_decode(heat.clone(), wh, reg=None, K=K).numpy(), g["dets_noreg"])

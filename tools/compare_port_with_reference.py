@@ -1,0 +1,28 @@
+"""Build-container only (needs /root/reference): runs the UNMODIFIED reference ctdet_decode and the timed CPU port
+(oracle/torch_port.py) on the same synthetic batch, checks the outputs are identical and prints both times, so the
+`cpu_baseline` / `--impl reference` numbers of bench.py (which cannot import the reference on the GPU box) are
+anchored to the real thing."""
+import os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference/src/lib')
+from models.decode import ctdet_decode as ref_decode          # the reference, unmodified
+from oracle.torch_port import ctdet_decode as port_decode
+
+threads = int(sys.argv[1]) if len(sys.argv) > 1 else (os.cpu_count() or 1)
+torch.set_num_threads(threads)
+torch.manual_seed(317)
+B = 64
+heat = torch.sigmoid(torch.randn(B, 80, 128, 128) - 2.19)
+wh = torch.rand(B, 2, 128, 128) * 32
+reg = torch.rand(B, 2, 128, 128)
+a = ref_decode(heat.clone(), wh, reg=reg, K=100)
+b = port_decode(heat.clone(), wh, reg=reg, K=100)
+print('identical outputs:', torch.equal(a, b))
+for name, fn in (('reference', ref_decode), ('port', port_decode)):
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter(); fn(heat, wh, reg=reg, K=100); ts.append(time.perf_counter() - t0)
+    ts.sort()
+    print('%-9s B=%d threads=%d: median %.3f s = %.1f img/s' % (name, B, threads, ts[2], B / ts[2]))
