@@ -20,9 +20,11 @@ reg = torch.rand(B, 2, 128, 128)
 a = ref_decode(heat.clone(), wh, reg=reg, K=100)
 b = port_decode(heat.clone(), wh, reg=reg, K=100)
 print('identical outputs:', torch.equal(a, b))
-for name, fn in (('reference', ref_decode), ('port', port_decode)):
-    ts = []
-    for _ in range(5):
-        t0 = time.perf_counter(); fn(heat, wh, reg=reg, K=100); ts.append(time.perf_counter() - t0)
+res = {'reference': [], 'port': []}
+for rep in range(8):   # alternate the order: the first call of a pair warms the caches for the second
+    pair = (('reference', ref_decode), ('port', port_decode))
+    for name, fn in (pair if rep % 2 == 0 else pair[::-1]):
+        t0 = time.perf_counter(); fn(heat, wh, reg=reg, K=100); res[name].append(time.perf_counter() - t0)
+for name, ts in res.items():
     ts.sort()
-    print('%-9s B=%d threads=%d: median %.3f s = %.1f img/s' % (name, B, threads, ts[2], B / ts[2]))
+    print('%-9s B=%d threads=%d: median %.3f s = %.1f img/s (min %.3f s)' % (name, B, threads, ts[len(ts) // 2], B / ts[len(ts) // 2], ts[0]))
