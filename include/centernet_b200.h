@@ -183,9 +183,13 @@ int cnb_reg_loss(const float *output, const void *mask, const int64_t *ind, cons
  * `columns` / `ones` scratch.  input [b,cin,h,w], offset [b,2*kh*kw*dg,ho,wo]
  * (channel 2t = dy, 2t+1 = dx of tap t), mask [b,kh*kw*dg,ho,wo],
  * weight [cout,cin,kh,kw], bias [cout] -> output [b,cout,ho,wo].
- * Backward ACCUMULATES into grad_weight/grad_bias and overwrites
- * grad_input/grad_offset/grad_mask, which must arrive zero-filled as in
- * dcn_v2_func.py:44-48. */
+ * Backward ACCUMULATES into grad_weight/grad_bias and into
+ * grad_input/grad_offset/grad_mask, all of which must arrive zero-filled as in
+ * dcn_v2_func.py:44-48.
+ * Forward workspace (cnb_dcnv2_workspace_bytes, 16-byte aligned): the weights
+ * re-tiled for the tensor-core path plus a channels-last copy of the input;
+ * the query returns 0 for kernels with more than 9 taps.  workspace == NULL
+ * (or smaller than the query) selects the fp32 CUDA-core forward instead. */
 size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
                                  int stride, int pad, int dil, int dg);
 int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask,
