@@ -74,6 +74,23 @@ __global__ void __launch_bounds__(256) k_gather_feat(const float *__restrict__ f
   }
 }
 
+// grad_feat[b, ch, ind[b, m]] += grad_out[b, m, ch]: the adjoint of the gather (autograd of `feat.gather(1, ind)`,
+// models/utils.py:15).  An index may repeat inside an image, hence the atomic add; grad_feat arrives zero-filled.
+__global__ void __launch_bounds__(256) k_gather_feat_bwd(const float *__restrict__ grad_out,
+                                                         const int64_t *__restrict__ ind,
+                                                         float *__restrict__ grad_feat, int B, int C, long long HW,
+                                                         int M) {
+  const long long total = (long long)B * M * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C);
+    const long long bm = i / C;
+    const int b = (int)(bm / M);
+    const long long sp = ind[bm];
+    if (sp >= 0 && sp < HW) atomicAdd(grad_feat + ((long long)b * C + ch) * HW + sp, grad_out[i]);
+  }
+}
+
 // ------------------------------------------------------------------ A9: ddd epilogue
 // models/decode.py:432-460: [xs, ys, score, rot(8), depth, dim(3), (wh(2)), cls]
 __global__ void __launch_bounds__(128) k_ddd_epilogue(const float *__restrict__ scores,
@@ -158,6 +175,18 @@ int cnb_nms(const float *heat, float *out, int n, int c, int h, int w, void *str
   else
     k_nms<false><<<grid, 256, 0, (cudaStream_t)stream>>>(heat, out, planes, h, w);
   CNB_CHECK_LAUNCH("cnb_nms");
+  count_launch();
+  return CNB_OK;
+}
+
+int cnb_gather_feat_backward(const float *grad_out, const int64_t *ind, float *grad_feat, int b, int c, int hw, int m,
+                             void *stream) {
+  CNB_REQUIRE(grad_out && ind && grad_feat, CNB_EINVAL, "cnb_gather_feat_backward: null pointer");
+  CNB_REQUIRE(b > 0 && c > 0 && hw > 0 && m > 0, CNB_EINVAL, "cnb_gather_feat_backward: non-positive dimension");
+  const long long total = (long long)b * m * c;
+  const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+  k_gather_feat_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(grad_out, ind, grad_feat, b, c, hw, m);
+  CNB_CHECK_LAUNCH("cnb_gather_feat_backward");
   count_launch();
   return CNB_OK;
 }

@@ -56,6 +56,11 @@ PYBIND11_MODULE(_C, m) {
                           ptr<void>(stream)),
           "cnb_gather_feat");
   });
+  m.def("gather_feat_backward", [](P gout, P ind, P gfeat, int b, int c, int hw, int mm, P stream) {
+    check(cnb_gather_feat_backward(ptr<const float>(gout), ptr<const int64_t>(ind), ptr<float>(gfeat), b, c, hw, mm,
+                                   ptr<void>(stream)),
+          "cnb_gather_feat_backward");
+  });
   m.def("ctdet_decode", [](P heat, P wh, P reg, int cat, int b, int c, int h, int w, int k, P dets, P ws, size_t wsb,
                            P stream) {
     check(cnb_ctdet_decode(ptr<const float>(heat), ptr<const float>(wh), ptr<const float>(reg), cat, b, c, h, w, k,

@@ -232,7 +232,10 @@ def exct_decode(t_heat, l_heat, b_heat, r_heat, ct_heat, t_regr=None, l_regr=Non
 
 
 # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
-_HOST_CTX = {}
+import threading
+
+_HOST_TLS = threading.local()   # staging buffers, events and the copy stream are PER THREAD (one thread per GPU
+                                # in DataParallel-style callers): nothing here is shared between threads
 
 
 def ctdet_decode_from_host(heat, wh, reg=None, cat_spec_wh=False, K=100, chunk=8, device=None):
@@ -240,7 +243,8 @@ def ctdet_decode_from_host(heat, wh, reg=None, cat_spec_wh=False, K=100, chunk=8
     `chunk`-image pieces whose H2D copies run on a side stream, double-buffered against the
     decode kernels of the previous piece; the [B, K, 6] detections come back in pinned host
     memory.  This is the call a detector makes when the heat maps are produced off-device
-    (and what bench.py times as `e2e`).  Same semantics as ctdet_decode."""
+    (and what bench.py times as `e2e`).  Same semantics as ctdet_decode: the result is a FRESH host
+    tensor the caller owns (the pinned staging buffer is copied out, 2.4 KB per image)."""
     if heat.is_cuda:
         return ctdet_decode(heat, wh, reg=reg, cat_spec_wh=cat_spec_wh, K=K).cpu()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -248,7 +252,10 @@ def ctdet_decode_from_host(heat, wh, reg=None, cat_spec_wh=False, K=100, chunk=8
     b, c, h, w = _dims(heat)
     chunk = max(1, min(chunk, b))
     key = (dev.index, c, h, w, int(wh.shape[1]), reg is not None, chunk, b, K)
-    ctx = _HOST_CTX.get(key)
+    cache = getattr(_HOST_TLS, "ctx", None)
+    if cache is None:
+        cache = _HOST_TLS.ctx = {}
+    ctx = cache.get(key)
     if ctx is None:
         ctx = {
             "copy": torch.cuda.Stream(device=dev),
@@ -262,8 +269,8 @@ def ctdet_decode_from_host(heat, wh, reg=None, cat_spec_wh=False, K=100, chunk=8
             "free": [torch.cuda.Event(), torch.cuda.Event()],
             "ready": [torch.cuda.Event(), torch.cuda.Event()],
         }
-        _HOST_CTX.clear()  # keep one geometry resident
-        _HOST_CTX[key] = ctx
+        cache.clear()  # keep one geometry resident per thread
+        cache[key] = ctx
     main = torch.cuda.current_stream(dev)
     copy = ctx["copy"]
     copy.wait_stream(main)
@@ -286,4 +293,4 @@ def ctdet_decode_from_host(heat, wh, reg=None, cat_spec_wh=False, K=100, chunk=8
         ctx["free"][slot].record(main)
     ctx["out"].copy_(ctx["dets"], non_blocking=True)
     main.synchronize()
-    return ctx["out"]
+    return ctx["out"].clone()

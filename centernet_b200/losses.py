@@ -156,3 +156,49 @@ class RegWeightedL1Loss(nn.Module):
 
     def forward(self, output, mask, ind, target):
         return _RegFn.apply(output, mask, ind, target, 3)
+
+
+# ------------------------------------------------------------------ ddd-only ride-alongs (trains/ddd.py:14)
+# Not on the heat-map hot path (SURVEY 8a stops at A16): kept so that a full overlay of models/losses.py
+# exports every class the trainers import.  The gather is the library's kernel (differentiable); the few
+# hundred gathered values are reduced with stock tensor ops.
+from .utils import _transpose_and_gather_feat  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+
+class L1Loss(nn.Module):
+    """models/losses.py:177-185 (mean over all B*M*D elements of the masked L1)."""
+
+    def forward(self, output, mask, ind, target):
+        pred = _transpose_and_gather_feat(output, ind)
+        m = mask.unsqueeze(2).expand_as(pred).float()
+        return F.l1_loss(pred * m, target * m, reduction="mean")
+
+
+def compute_rot_loss(output, target_bin, target_res, mask):
+    """models/losses.py:205-237: two orientation bins, each a 2-way classification (cross entropy on the
+    mask-zeroed logits, mean over all rows) plus smooth-L1 on sin/cos of the residual over the rows whose
+    bin label is set (mean over those rows, skipped when there are none)."""
+    output = output.reshape(-1, 8)
+    target_bin = target_bin.reshape(-1, 2)
+    target_res = target_res.reshape(-1, 2)
+    m = mask.reshape(-1, 1).float()
+    total = output.new_zeros(())
+    for k in range(2):
+        logits = output[:, 4 * k:4 * k + 2] * m
+        total = total + F.cross_entropy(logits, target_bin[:, k].long(), reduction="mean")
+        rows = target_bin[:, k].nonzero()[:, 0]
+        if rows.numel() > 0:
+            o = output.index_select(0, rows)
+            r = target_res.index_select(0, rows)[:, k]
+            total = total + F.smooth_l1_loss(o[:, 4 * k + 2], torch.sin(r), reduction="mean") \
+                          + F.smooth_l1_loss(o[:, 4 * k + 3], torch.cos(r), reduction="mean")
+    return total
+
+
+class BinRotLoss(nn.Module):
+    """models/losses.py:187-194."""
+
+    def forward(self, output, mask, ind, rotbin, rotres):
+        pred = _transpose_and_gather_feat(output, ind)
+        return compute_rot_loss(pred, rotbin, rotres, mask)

@@ -21,18 +21,43 @@ def _gather_feat(feat, ind, mask=None):
     return feat
 
 
+class _TransposeGather(torch.autograd.Function):
+    """Differentiable like the reference's permute + gather: the losses of models/losses.py
+    (RegL1Loss, RegLoss, NormRegL1Loss, RegWeightedL1Loss, L1Loss, BinRotLoss) back-propagate
+    through `pred = _transpose_and_gather_feat(output, ind)`."""
+
+    @staticmethod
+    def forward(ctx, feat, ind):
+        f = f32c(feat)
+        ind = ind.contiguous().long()
+        B, Cc, H, W = f.shape
+        M = ind.shape[1]
+        out = torch.empty((B, M, Cc), dtype=torch.float32, device=f.device)
+        if B * M * Cc:
+            C.gather_feat(ptr(f), ptr(ind), ptr(out), B, Cc, H * W, M, stream_ptr(f))
+        ctx.save_for_backward(ind)
+        ctx.shape = (B, Cc, H, W)
+        ctx.in_dtype = feat.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (ind,) = ctx.saved_tensors
+        B, Cc, H, W = ctx.shape
+        g = f32c(grad_out)
+        grad_feat = torch.zeros((B, Cc, H, W), dtype=torch.float32, device=g.device)
+        M = ind.shape[1]
+        if B * M * Cc:
+            C.gather_feat_backward(ptr(g), ptr(ind), ptr(grad_feat), B, Cc, H * W, M, stream_ptr(g))
+        return grad_feat.to(ctx.in_dtype), None
+
+
 def _transpose_and_gather_feat(feat, ind):
     """models/utils.py:22-26, without the full NCHW->NHWC transpose copy: the kernel
-    reads feat[b, :, ind[b, m]] directly.  feat [B, C, H, W], ind [B, M] -> [B, M, C]."""
+    reads feat[b, :, ind[b, m]] directly.  feat [B, C, H, W], ind [B, M] -> [B, M, C].
+    Differentiable w.r.t. feat (scatter-add adjoint, cnb_gather_feat_backward)."""
     require_cuda(feat, ind, what="_transpose_and_gather_feat")
-    feat = f32c(feat)
-    ind = ind.contiguous().long()
-    B, Cc, H, W = feat.shape
-    M = ind.shape[1]
-    out = torch.empty((B, M, Cc), dtype=torch.float32, device=feat.device)
-    if B * M * Cc:
-        C.gather_feat(ptr(feat), ptr(ind), ptr(out), B, Cc, H * W, M, stream_ptr(feat))
-    return out
+    return _TransposeGather.apply(feat, ind)
 
 
 def flip_tensor(x):

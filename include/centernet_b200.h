@@ -80,6 +80,13 @@ int cnb_topk_channel(const float *scores, int b, int c, int h, int w, int k, int
  * copy: out[b, m, ch] = feat[b, ch, ind[b, m]];  feat [b, c, h*w], ind [b, m]. */
 int cnb_gather_feat(const float *feat, const int64_t *ind, float *out,
                     int b, int c, int hw, int m, void *stream);
+/* Adjoint of cnb_gather_feat (what autograd derives for the reference's
+ * permute + gather, models/utils.py:12-26; used by every Reg*Loss, L1Loss and
+ * BinRotLoss of models/losses.py through `pred = _transpose_and_gather_feat`):
+ * grad_feat[b, ch, ind[b, m]] += grad_out[b, m, ch].  grad_feat must arrive
+ * zero-filled; repeated indices accumulate. */
+int cnb_gather_feat_backward(const float *grad_out, const int64_t *ind, float *grad_feat,
+                             int b, int c, int hw, int m, void *stream);
 
 /* ---------------------------------------------------------- A5: ctdet_decode
  * models/decode.py:464-495.  heat [b,c,h,w] (post-sigmoid), wh [b,2,h,w] (or

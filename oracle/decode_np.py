@@ -237,39 +237,61 @@ def _exct_core(t_heat, l_heat, b_heat, r_heat, ct_heat, regs, K, scores_thresh,
         n[n > 1] = 1
         ext.append(topk(n, K))
     (ts, ti, tc, ty, tx), (ls, li, lc, ly, lx), (bs, bi, bc, by, bx), (rs, ri, rc, ry, rx) = ext
-    sh = lambda a, ax: a.reshape([B] + [K if i == ax else 1 for i in range(4)])
-    ty_, tx_, ts_, tc_ = sh(ty, 0), sh(tx, 0), sh(ts, 0), sh(tc, 0)
-    ly_, lx_, ls_, lc_ = sh(ly, 1), sh(lx, 1), sh(ls, 1), sh(lc, 1)
-    by_, bx_, bs_, bc_ = sh(by, 2), sh(bx, 2), sh(bs, 2), sh(bc, 2)
-    ry_, rx_, rs_, rc_ = sh(ry, 3), sh(rx, 3), sh(rs, 3), sh(rc, 3)
-    full = (B, K, K, K, K)
-    cx = ((lx_ + rx_ + F32(0.5)) / F32(2)).astype(np.int64)          # :322-323
-    cy = ((ty_ + by_ + F32(0.5)) / F32(2)).astype(np.int64)
-    cx = np.broadcast_to(cx, full); cy = np.broadcast_to(cy, full)
-    bidx = np.arange(B).reshape(B, 1, 1, 1, 1)
     if agnostic:                                                       # :159,175-180
         agn = ct_heat.max(axis=1); agn_cls = ct_heat.argmax(axis=1)
-        ct = agn[bidx, cy, cx]
-        clses = agn_cls[bidx, cy, cx].astype(F32)
-    else:                                                              # :324-327
-        tcl = np.broadcast_to(tc_.astype(np.int64), full)
-        ct = ct_heat[bidx, tcl, cy, cx]
-        clses = np.broadcast_to(tc_.astype(F32), full)
-    scores = ((((ts_ + ls_) + bs_) + rs_) + F32(2) * ct) / F32(6)      # :333 / :192
-    sc_bad = ((ts_ < F32(scores_thresh)) | (ls_ < F32(scores_thresh)) |
-              (bs_ < F32(scores_thresh)) | (rs_ < F32(scores_thresh)) |
-              (ct < F32(center_thresh)))
-    top_bad = (ty_ > ly_) | (ty_ > by_) | (ty_ > ry_)
-    left_bad = (lx_ > tx_) | (lx_ > bx_) | (lx_ > rx_)
-    bot_bad = (by_ < ty_) | (by_ < ly_) | (by_ < ry_)
-    right_bad = (rx_ < tx_) | (rx_ < lx_) | (rx_ < bx_)
-    scores = scores - np.broadcast_to(sc_bad, full).astype(F32)
-    if not agnostic:
-        cls_bad = (tc_ != lc_) | (tc_ != bc_) | (tc_ != rc_)
-        scores = scores - np.broadcast_to(cls_bad, full).astype(F32)
-    for bad in (top_bad, left_bad, bot_bad, right_bad):
-        scores = scores - np.broadcast_to(bad, full).astype(F32)
-    scores, sel = _stable_topk(scores.reshape(B, -1), num_dets)         # :362-364
+    bidx = np.arange(B).reshape(B, 1, 1, 1, 1)
+
+    def slab(t0, t1):
+        """Scores and classes of the tuples whose t index lies in [t0, t1): [B, (t1-t0)*K^3] each.
+        The reference materialises all K^4 at once (:309-360); slabs keep the oracle inside a few
+        hundred MB at K=100 without changing a single per-tuple operation."""
+        n = t1 - t0
+        sh = lambda a, ax: a.reshape([B] + [(n if ax == 0 else K) if i == ax else 1 for i in range(4)])
+        ty_, tx_, ts_, tc_ = [sh(a[:, t0:t1], 0) for a in (ty, tx, ts, tc)]
+        ly_, lx_, ls_, lc_ = sh(ly, 1), sh(lx, 1), sh(ls, 1), sh(lc, 1)
+        by_, bx_, bs_, bc_ = sh(by, 2), sh(bx, 2), sh(bs, 2), sh(bc, 2)
+        ry_, rx_, rs_, rc_ = sh(ry, 3), sh(rx, 3), sh(rs, 3), sh(rc, 3)
+        full = (B, n, K, K, K)
+        cx = ((lx_ + rx_ + F32(0.5)) / F32(2)).astype(np.int64)          # :322-323
+        cy = ((ty_ + by_ + F32(0.5)) / F32(2)).astype(np.int64)
+        cx = np.broadcast_to(cx, full); cy = np.broadcast_to(cy, full)
+        if agnostic:
+            ct = agn[bidx, cy, cx]
+            clses = agn_cls[bidx, cy, cx].astype(F32)
+        else:                                                              # :324-327
+            tcl = np.broadcast_to(tc_.astype(np.int64), full)
+            ct = ct_heat[bidx, tcl, cy, cx]
+            clses = np.broadcast_to(tc_.astype(F32), full)
+        scores = ((((ts_ + ls_) + bs_) + rs_) + F32(2) * ct) / F32(6)      # :333 / :192
+        sc_bad = ((ts_ < F32(scores_thresh)) | (ls_ < F32(scores_thresh)) |
+                  (bs_ < F32(scores_thresh)) | (rs_ < F32(scores_thresh)) |
+                  (ct < F32(center_thresh)))
+        top_bad = (ty_ > ly_) | (ty_ > by_) | (ty_ > ry_)
+        left_bad = (lx_ > tx_) | (lx_ > bx_) | (lx_ > rx_)
+        bot_bad = (by_ < ty_) | (by_ < ly_) | (by_ < ry_)
+        right_bad = (rx_ < tx_) | (rx_ < lx_) | (rx_ < bx_)
+        scores = scores - np.broadcast_to(sc_bad, full).astype(F32)
+        if not agnostic:
+            cls_bad = (tc_ != lc_) | (tc_ != bc_) | (tc_ != rc_)
+            scores = scores - np.broadcast_to(cls_bad, full).astype(F32)
+        for bad in (top_bad, left_bad, bot_bad, right_bad):
+            scores = scores - np.broadcast_to(bad, full).astype(F32)
+        return scores.reshape(B, -1), np.asarray(clses).reshape(B, -1)
+
+    # topk(num_dets) over all K^4 tuples (:362-364) = top of the union of per-slab tops; slabs are
+    # visited in ascending tuple index, so the stable final sort keeps (score desc, index asc).
+    step = max(1, min(K, (4 << 20) // (K * K * K)))
+    cs, ci, cc = [], [], []
+    for t0 in range(0, K, step):
+        s_, c_ = slab(t0, min(K, t0 + step))
+        v, o = _stable_topk(s_, min(num_dets, s_.shape[1]))
+        o = np.sort(o, axis=1)                                         # back to index order inside the slab
+        cs.append(np.take_along_axis(s_, o, axis=1)); cc.append(np.take_along_axis(c_, o, axis=1))
+        ci.append(o + t0 * K * K * K)
+    cs, ci, cc = np.concatenate(cs, 1), np.concatenate(ci, 1), np.concatenate(cc, 1)
+    scores, pick = _stable_topk(cs, num_dets)
+    sel = np.take_along_axis(ci, pick, axis=1)
+    clses_sel = np.take_along_axis(cc, pick, axis=1)
     if all(r is not None for r in regs):                                # :366-384
         tr, lr, br, rr = [transpose_and_gather_feat(np.asarray(r, F32), i)
                           for r, i in zip(regs, (ti, li, bi, ri))]
@@ -283,7 +305,7 @@ def _exct_core(t_heat, l_heat, b_heat, r_heat, ct_heat, regs, K, scores_thresh,
         bx2, by2, rx2, ry2 = bx + h, by + h, rx + h, ry + h
     i_t = sel // (K * K * K); i_l = (sel // (K * K)) % K; i_b = (sel // K) % K; i_r = sel % K
     g = lambda a, i: np.take_along_axis(a, i, axis=1)
-    clses = np.take_along_axis(clses.reshape(B, -1), sel, axis=1)
+    clses = clses_sel
     cols = [g(lx2, i_l), g(ty2, i_t), g(rx2, i_r), g(by2, i_b), scores,
             g(tx2, i_t), g(ty2, i_t), g(lx2, i_l), g(ly2, i_l),
             g(bx2, i_b), g(by2, i_b), g(rx2, i_r), g(ry2, i_r), clses]
