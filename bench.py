@@ -35,6 +35,41 @@ N_ROT = 3                                                      # rotating input 
 NCU_TRAFFIC_BYTES = 338720512 + 4057088                        # measured DRAM read + write of one launch (profiles/)
 
 
+def workload_config(world):
+    """The SAME dict in both arms (the driver compares them): what one step processes."""
+    return {
+        "workload": "ctdet decode, %d img/GPU x %dx%dx%d post-sigmoid heat + wh + reg, K=%d "
+                    "(BASELINE configs[1] geometry: DLA-34 512x512 batch=64 heads)" % (B_PER_GPU, C, H, W, K),
+        "global_batch": B_PER_GPU * world,
+        "parallelism": "dp%d (batch shards, no collective)" % world,
+        "l2": "inputs > L2: %d rotating batches of %.0f MB" % (N_ROT, B_PER_GPU * (C + 4) * H * W * 4 / 1e6),
+    }
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank (and the pinned host buffers it allocates afterwards, first touch) to the NUMA node its
+    GPU hangs off: at N=8 the eight H2D streams otherwise fight over one socket's memory controllers.
+    Returns a short description for the JSON line."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa_node unknown (single node)"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return "bound to NUMA node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+
+
 def synth(batch, device, seed):
     """SURVEY.md section 8d synthetic inputs: heat = sigmoid(randn - 2.19), wh = rand*32, reg = rand."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -50,7 +85,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-        self.recording = False      # only samples taken inside the timed region are kept
+        self.recording = False      # only samples taken inside the timed region are kept ...
+        self.sample_now = False     # ... plus one forced sample right before it (GPU under warm-up load) and after it
         self.alive = threading.Event()
 
     def run(self):
@@ -72,15 +108,24 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.alive.set()
-                if self.recording:
+                if self.recording or self.sample_now:
+                    self.sample_now = False
                     self.samples.append(mhz)
                     for bit, name in names.items():
                         if r & bit:
                             self.reasons.add(name)
-                time.sleep(0.002)
+                if not self.recording:
+                    time.sleep(0.0005)          # back-to-back NVML reads (~50 us each) inside the timed region
         except Exception as e:  # no NVML: report that instead of inventing numbers
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
             self.alive.set()
+
+    def force_sample(self):
+        """One synchronous sample (the driver's 20-step region lasts < 2 ms, shorter than a scheduling quantum)."""
+        self.sample_now = True
+        t0 = time.perf_counter()
+        while self.sample_now and time.perf_counter() - t0 < 0.05 and self.is_alive():
+            time.sleep(0.0002)
 
     def summary(self):
         s = sorted(self.samples)
@@ -154,8 +199,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ctdet decode, %d img x %dx%dx%d heat + wh + reg, K=%d (BASELINE configs[1] geometry)"
-                   % (B_PER_GPU, C, H, W, K), "global_batch": B_PER_GPU * args.gpus},
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -170,6 +214,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the per-kernel secondary measurements (N=1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -185,6 +230,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)      # before any pinned allocation (first touch decides the node)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -207,6 +253,9 @@ def main():
     sampler.start()
     sampler.alive.wait(timeout=10)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3):                      # keep the GPU under load while the "before" sample is taken
+        D.ctdet_decode(*batches[i % N_ROT][:2], reg=batches[i % N_ROT][2], K=K)
+    sampler.force_sample()
     barrier()
     l0 = CL.launch_count()
     sampler.recording = True
@@ -217,12 +266,17 @@ def main():
     ev1.record()
     barrier()
     sampler.recording = False
+    sampler.force_sample()
     launches = CL.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     t = torch.tensor([ms], device=dev)
+    per_rank_ms = [ms]
     if world > 1:
+        allms = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(allms, t)
+        per_rank_ms = [float(x.item()) for x in allms]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = B_PER_GPU * world * args.steps / (ms_max * 1e-3)
@@ -266,10 +320,25 @@ def main():
         barrier()
         e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
         t = torch.tensor([e2e_ms], device=dev)
+        e2e_rank_ms = [e2e_ms]
         if world > 1:
+            allms = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(allms, t)
+            e2e_rank_ms = [float(x.item()) for x in allms]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = B_PER_GPU * world * args.e2e_steps / (float(t.item()) * 1e-3)
+        h2d_gbs_per_rank = [round(h2d * args.e2e_steps / (m * 1e-3) / 1e9, 2) for m in e2e_rank_ms]
+        del host
 
+    secondary = {"ctdet_decode_from_logits": {"value": logit_value, "unit": UNIT,
+                                              "note": "same workload, input = pre-sigmoid logits, sigmoid fused "
+                                                      "into the selection kernel (one launch, no heat map written)"}}
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            import bench_secondary
+            secondary.update(bench_secondary.run(dev, batches, K=K, steps=min(max(args.steps, 5), 20)))
+        except Exception as e:
+            secondary["failed"] = str(e)[:200]
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         # the decode call is ONE kernel launch in this geometry (k_select_hot: NMS + top-K + gathers +
@@ -280,12 +349,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "ctdet decode, %d img/GPU x %dx%dx%d post-sigmoid heat + wh + reg, K=%d "
-                            "(BASELINE configs[1] geometry: DLA-34 512x512 batch=64 heads)" % (B_PER_GPU, C, H, W, K),
-                "global_batch": B_PER_GPU * world, "parallelism": "dp%d (batch shards, no collective)" % world,
-                "l2": "inputs > L2: %d rotating batches of %.0f MB" % (N_ROT, h2d / 1e6),
-            },
+            "config": workload_config(world),
+            "per_rank_ms_per_step": [round(m / args.steps, 5) for m in per_rank_ms],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
                          "traffic_source": "profiles/r1_decode_hot_final_summary.csv (ncu --set full: "
@@ -293,11 +358,12 @@ def main():
                          "kernel": "k_select_hot (the whole decode call is this one launch)",
                          "alg_bytes_per_launch": ALG_BYTES_PER_IMAGE * B_PER_GPU},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps},
+                    "steps": args.e2e_steps,
+                    "h2d_gbs_per_rank": h2d_gbs_per_rank if args.e2e_steps > 0 else None, "host_binding": numa,
+                    "bound_by": "PCIe Gen5 x16 host->device copy of the fp32 heat/wh/reg batch (352 MB per step, "
+                                "pinned, chunked and overlapped with the decode); the decode itself is ~1% of it"},
             "gpu_launches": int(launches),
-            "secondary": {"ctdet_decode_from_logits": {"value": logit_value, "unit": UNIT,
-                                                       "note": "same workload, input = pre-sigmoid logits, sigmoid fused "
-                                                               "into the selection kernel (one launch, no heat map written)"}},
+            "secondary": secondary,
             "clocks": sampler.summary(),
             "lib_version": centernet_b200.version(),
         }

@@ -486,7 +486,15 @@ static int check_shape(const char *fn, int b, int cin, int h, int w, int cout, i
 }  // namespace cnb
 
 namespace cnb {
-size_t dcn_tc_workspace_bytes(int b, int cin, int h, int w, int cout, int dg);
+size_t dcn_tc_workspace_bytes(int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int ph, int dh, int dg);
+size_t dcn_tc_fwd_workspace_bytes(int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int ph, int dh, int dg);
+size_t dcn_tc_wtiles_bytes(int cin, int cout, int dg);
+int dcn_prepare_weights_tc(const float *weight, int cin, int cout, int kh, int kw, int dg, float *wtiles,
+                           cudaStream_t stream);
+int dcn_forward_tc_prepared(const float *input, int input_nhwc, const float *offset, const float *mask,
+                            const float *wtiles, const float *bias, float *output, int b, int cin, int h, int w,
+                            int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
+                            void *workspace, cudaStream_t stream);
 int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
                    const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
                    int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream);
@@ -499,9 +507,64 @@ extern "C" {
 // No column / ones scratch (the reference's `columns`, `ones`): the workspace holds the weights re-tiled
 // (TF32 hi/lo split, UMMA layout) and a channels-last copy of the input for the tensor-core forward.  Passing workspace == NULL
 // (or too small) to cnb_dcnv2_forward selects the fp32 CUDA-core kernel instead.
-size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw, int, int, int, int dg) {
-  if (b <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX) return 0;
-  return dcn_tc_workspace_bytes(b, cin, h, w, cout, dg);
+size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw, int stride, int pad, int dil,
+                                 int dg) {
+  if (b <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX ||
+      stride <= 0 || dil <= 0 || pad < 0)
+    return 0;
+  return dcn_tc_workspace_bytes(b, cin, h, w, cout, kh, kw, stride, pad, dil, dg);
+}
+
+size_t cnb_dcnv2_wtiles_bytes(int cin, int cout, int kh, int kw, int dg) {
+  if (cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX) return 0;
+  return dcn_tc_wtiles_bytes(cin, cout, dg);
+}
+
+int cnb_dcnv2_prepare_weights(const float *weight, int cin, int cout, int kh, int kw, int deformable_groups,
+                              void *wtiles, size_t wtiles_bytes, void *stream) {
+  CNB_REQUIRE(weight && wtiles, CNB_EINVAL, "cnb_dcnv2_prepare_weights: null pointer");
+  CNB_REQUIRE(cin > 0 && cout > 0 && kh > 0 && kw > 0 && deformable_groups > 0 && cin % deformable_groups == 0,
+              CNB_EINVAL, "cnb_dcnv2_prepare_weights: bad shape");
+  CNB_REQUIRE(kh * kw <= DCN_KT_MAX, CNB_EUNSUPPORTED, "cnb_dcnv2_prepare_weights: more than %d taps", DCN_KT_MAX);
+  CNB_REQUIRE(wtiles_bytes >= dcn_tc_wtiles_bytes(cin, cout, deformable_groups), CNB_EWORKSPACE,
+              "cnb_dcnv2_prepare_weights: buffer %zu < %zu", wtiles_bytes,
+              dcn_tc_wtiles_bytes(cin, cout, deformable_groups));
+  CNB_REQUIRE((reinterpret_cast<uintptr_t>(wtiles) & 15u) == 0, CNB_EINVAL,
+              "cnb_dcnv2_prepare_weights: buffer must be 16-byte aligned");
+  return dcn_prepare_weights_tc(weight, cin, cout, kh, kw, deformable_groups, reinterpret_cast<float *>(wtiles),
+                                (cudaStream_t)stream);
+}
+
+size_t cnb_dcnv2_prepared_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw, int stride, int pad,
+                                          int dil, int dg) {
+  if (b <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX ||
+      stride <= 0 || dil <= 0 || pad < 0)
+    return 0;
+  return dcn_tc_fwd_workspace_bytes(b, cin, h, w, cout, kh, kw, stride, pad, dil, dg);
+}
+
+int cnb_dcnv2_forward_prepared(const float *input, int input_channels_last, const float *offset, const float *mask,
+                               const void *wtiles, const float *bias, float *output, int b, int cin, int h, int w,
+                               int cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
+                               int dil_w, int deformable_groups, void *workspace, size_t workspace_bytes,
+                               void *stream_) {
+  CNB_REQUIRE(input && offset && mask && wtiles && output && workspace, CNB_EINVAL,
+              "cnb_dcnv2_forward_prepared: null pointer");
+  DcnShape s;
+  int rc = check_shape("cnb_dcnv2_forward_prepared", b, cin, h, w, cout, kh, kw, stride_h, stride_w, pad_h, pad_w,
+                       dil_h, dil_w, deformable_groups, &s);
+  if (rc != CNB_OK) return rc;
+  CNB_REQUIRE(stride_h == stride_w && pad_h == pad_w && dil_h == dil_w, CNB_EUNSUPPORTED,
+              "cnb_dcnv2_forward_prepared: anisotropic stride/pad/dilation");
+  CNB_REQUIRE(workspace_bytes >= dcn_tc_fwd_workspace_bytes(b, cin, h, w, cout, kh, kw, stride_h, pad_h, dil_h,
+                                                            deformable_groups),
+              CNB_EWORKSPACE, "cnb_dcnv2_forward_prepared: workspace too small");
+  CNB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 && (reinterpret_cast<uintptr_t>(wtiles) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(input) & 15u) == 0,
+              CNB_EINVAL, "cnb_dcnv2_forward_prepared: buffers must be 16-byte aligned");
+  return dcn_forward_tc_prepared(input, input_channels_last, offset, mask, reinterpret_cast<const float *>(wtiles),
+                                 bias, output, b, cin, h, w, cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h,
+                                 dil_w, deformable_groups, workspace, (cudaStream_t)stream_);
 }
 
 int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask, const float *weight,
@@ -514,7 +577,8 @@ int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask
                        dil_w, deformable_groups, &s);
   if (rc != CNB_OK) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (workspace && workspace_bytes >= dcn_tc_workspace_bytes(b, cin, h, w, cout, deformable_groups) &&
+  if (workspace && stride_h == stride_w && pad_h == pad_w && dil_h == dil_w &&
+      workspace_bytes >= dcn_tc_workspace_bytes(b, cin, h, w, cout, kh, kw, stride_h, pad_h, dil_h, deformable_groups) &&
       (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0)
     return dcn_forward_tc(input, offset, mask, weight, bias, output, b, cin, h, w, cout, kh, kw, stride_h, stride_w,
                           pad_h, pad_w, dil_h, dil_w, deformable_groups, workspace, stream);

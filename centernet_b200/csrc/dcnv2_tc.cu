@@ -1,47 +1,65 @@
-// DCNv2 forward with the dense contraction on the 5th-generation tensor cores (tcgen05 / UMMA).
+// DCNv2 forward with the dense contraction on the 5th-generation tensor cores (tcgen05 / UMMA) -- a
+// persistent, warp-specialised pipeline (reference: dcn_v2_cuda.c:10-102 + dcn_v2_im2col_cuda.cu:118-180).
 //
-// Same decomposition as dcnv2.cu (a CTA owns 128 output pixels x 64|128 output channels, the
-// bilinear geometry of every (tap, pixel) is computed once, the sampled column tile of 8 input
-// channels is built in shared memory -- never in HBM), but the contraction
-//     D[128 pixels, Cout_tile] += col[128, 72] * W[Cout_tile, 72]^T
-// is issued by ONE thread as tcgen05.mma.kind::tf32 instructions (UTCHMMA in SASS), A and B both
-// K-major in the canonical no-swizzle shared-memory layout, the accumulator in TMEM (128 lanes x
-// Cout_tile fp32 columns), read back with tcgen05.ld for the bias + store epilogue.
+//   work item   = (image, 8x16 output-pixel tile [128 pixels = UMMA M], Cout tile of 64|128, K split)
+//   chunk       = 32 input channels x one tap: K = 32 of the contraction; chunks of an item run over
+//                 (channel block OUTER, tap INNER), so the ~40 KB input neighbourhood of a channel block is
+//                 fetched from L2 once and then re-read by all 9 taps x 4 bilinear corners out of L1
+//   sampler warps (16)  build the column tile col[128 px, 32 ch] of a chunk directly in shared memory
+//                 (never in HBM -- the reference writes and re-reads a 37.7 MB column matrix per sample),
+//                 split into TF32 hi/lo, in the canonical no-swizzle K-major UMMA layout; 3-deep ring
+//   TMA warp      streams the matching pre-split weight tile (hi+lo) with cp.async.bulk (UBLKCP)
+//   MMA warp      one thread issues tcgen05.mma.kind::tf32 (UTCHMMA): D[128, Cout_t] += col . W^T, three MMAs
+//                 per k-step (lo.hi + hi.lo + hi.hi = "3xTF32", fp32-accurate: the reference is an fp32
+//                 SGEMM and plain TF32 misses the 1e-4 bar at K = Cin*9 <= 4608); tcgen05.commit frees the
+//                 ring slot; accumulators live in TMEM, double-buffered across items
+//   epilogue warps (4)  tcgen05.ld the finished accumulator, add the bias and store NCHW while the
+//                 samplers are already on the next item
+// Nobody waits on anybody except through mbarriers; the only CTA-wide barriers are at start and end.
 //
-// Precision: the reference contraction is an fp32 SGEMM (dcn_v2_cuda.c:93-96).  Plain TF32 would
-// miss the 1e-4 bar for K = Cin*9 up to 4608, so every operand is split x = hi + lo with hi = x
-// truncated to TF32 (lo is exact in fp32) and three MMAs are accumulated: hi*hi + hi*lo + lo*hi
-// ("3xTF32"); the dropped lo*lo term and the TF32 rounding of lo are both ~2^-22 relative.
+// Sampling: the input is read from a channels-last copy [B][H*W][Cin/32][32] (k_dcn_nhwc; skipped when the
+// caller's tensor already is channels-last).  A warp gather covers 4 pixels x 32 channels with
+// lane = pixel * 8 + quad, so each quarter-warp -- the unit the L1 data pipe serves for 16-byte accesses --
+// reads ONE fully used 128-byte line (4 wavefronts per gather).  The UMMA tile wants the opposite lane order
+// (a quarter-warp = 8 rows of one k-chunk), so the reduced values are transposed across the warp with
+// shuffles before the conflict-free 16-byte stores.
 //
-// Sampling: the input is first re-laid channels-last (k_dcn_nhwc: [B][H*W][chunk][8 channels], one
-// coalesced pass), so one bilinear corner of a (pixel, tap) brings the 8 channels of the chunk with two
-// 16-byte loads from one 32-byte sector -- the NCHW layout needs 8 scalar loads from 8 different planes.
-// A work item is a (pixel, tap): 8 vector gathers, 32 FMAs, the TF32 split, four 16-byte stores into
-// the UMMA tile (K is ordered tap-major, k = tap * 8 + channel, so the 8 channels are two k-chunks).
+// Small maps (16x16, 8x8): too few tiles to fill 148 SMs, so the channel blocks of an item are split over
+// several CTAs (split-K); the partial sums go to the workspace and k_dcn_reduce adds them in a fixed order
+// (deterministic, no atomics).
 //
-// The weight tiles are pre-split and pre-tiled once per call by k_dcn_prep_weights into the
-// caller-provided workspace, so every chunk's B operand (hi + lo) arrives by two TMA bulk copies
-// (cp.async.bulk, UBLKCP) that overlap with the sampling of the A tile.
+// The weight tiles are pre-split / pre-tiled by k_dcn_prep_weights: once per call through the plain
+// cnb_dcnv2_forward, or once per weight version through cnb_dcnv2_prepare_weights +
+// cnb_dcnv2_forward_prepared (what the Python module does).
 #include "common.cuh"
 
 namespace cnb {
 
-constexpr int TC_TP = 128;        // pixels per CTA (UMMA M)
+constexpr int TC_TP = 128;        // pixels per item (UMMA M)
 constexpr int TC_CB = 32;         // input channels per chunk = one 128-byte line of the channels-last copy
-constexpr int TC_TG = 1;          // taps per chunk
-constexpr int TC_NTG = 9;         // tap groups (3x3 kernel)
-constexpr int TC_K = TC_CB * TC_TG;   // 32: K per chunk, k = channel_local
+constexpr int TC_NT = 9;          // taps (3x3 kernel; fewer taps leave zero weight tiles)
+constexpr int TC_K = TC_CB;       // K per chunk
 constexpr int TC_KC = TC_K / 4;   // 16-byte k-chunks
-constexpr int TC_THREADS = 512;       // 16 warps, two CTAs per SM: one samples while the other's MMAs run
+constexpr int TC_EPI_WARPS = 4;   // warps 0-3: TMEM lane quarter = warp index
+constexpr int TC_WARP_MMA = 4;
+constexpr int TC_WARP_TMA = 5;
+constexpr int TC_WARP_S0 = 6;     // first sampler warp
+constexpr int TC_SAMPLERS = 16;   // sampler warps: 2 warp items (4 pixels each) per warp and chunk
+constexpr int TC_THREADS = (TC_WARP_S0 + TC_SAMPLERS) * 32;   // 704
 constexpr uint32_t TC_LBO = 128;            // bytes between consecutive k-chunks (one 8 x 16 B core matrix)
 constexpr uint32_t TC_SBO = TC_KC * 128;    // bytes between 8-row groups
-constexpr int TC_A_BYTES = TC_TP * TC_K * 4;  // 16384
+constexpr int TC_A_BYTES = TC_TP * TC_K * 4;  // 16384 per hi / lo tile
 
 struct DcnShapeTc {
   int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo;
-  int co_t;       // output channels per CTA (64 or 128)
+  int co_t;       // output channels per item (64 or 128)
+  int n_cot;      // Cout tiles
   int cbs_pg;     // 32-channel blocks per deformable group
-  int n_chunks;   // chunks = dg * 9 taps * cbs_pg
+  int nb;         // channel blocks in total = dg * cbs_pg
+  int tw, th;     // pixel tile (tw * th == 128)
+  int tiles_x, tiles_y;
+  int splits;     // K splits (channel-block ranges) per item; > 1 -> partial sums + k_dcn_reduce
+  int n_items;    // B * tiles * n_cot * splits
 };
 
 struct __align__(16) TapMetaTc {
@@ -61,34 +79,39 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr) {
   return d;
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ void mbar_arrive_tc(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-// W[Cout][Cin][KT] -> per (cout tile, chunk): hi tile then lo tile, each [co_t][32] in the UMMA layout.
-// chunk = (group g, tap t, channel block cbi) in that nesting order; k = channel within the block.
+// W[Cout][Cin][KT] -> per (cout tile, channel block bi, tap): hi tile then lo tile, each [co_t][32] in the UMMA
+// layout; k = channel within the block.  Tile index = (cot * nb + bi) * 9 + tap.
 __global__ void __launch_bounds__(256) k_dcn_prep_weights(const float *__restrict__ w, const DcnShapeTc s,
                                                           float *__restrict__ ws) {
   const int KT = s.kh * s.kw;
   const int cpg = s.Cin / s.dg;
-  const int tile = blockIdx.x;                 // (cout tile, chunk)
-  const int cot = tile / s.n_chunks, ch = tile - cot * s.n_chunks;
-  const int per_g = TC_NTG * s.cbs_pg;
-  const int g = ch / per_g, r = ch - g * per_g;
-  const int tg = r / s.cbs_pg, cbi = r - tg * s.cbs_pg;
+  const int tile = blockIdx.x;
+  const int tap = tile % TC_NT, r = tile / TC_NT;
+  const int bi = r % s.nb, cot = r / s.nb;
+  const int g = bi / s.cbs_pg, cbi = bi - g * s.cbs_pg;
   const size_t tile_floats = (size_t)s.co_t * TC_K;
   unsigned char *hi = reinterpret_cast<unsigned char *>(ws + (size_t)tile * 2 * tile_floats);
   unsigned char *lo = hi + tile_floats * 4;
   for (int i = threadIdx.x; i < s.co_t * TC_K; i += blockDim.x) {
     const int o = i / TC_K, k = i - o * TC_K;
-    const int t = tg, cw = cbi * TC_CB + k;                    // tap, channel within the group
+    const int cw = cbi * TC_CB + k;                    // channel within the group
     float v = 0.f;
     const int oc = cot * s.co_t + o;
-    if (oc < s.Cout && cw < cpg && t < KT) v = w[((size_t)oc * s.Cin + g * cpg + cw) * KT + t];
+    if (oc < s.Cout && cw < cpg && tap < KT) v = w[((size_t)oc * s.Cin + g * cpg + cw) * KT + tap];
     const float h = tf32_hi(v);
     *reinterpret_cast<float *>(hi + tc_tile_off(o, k)) = h;
     *reinterpret_cast<float *>(lo + tc_tile_off(o, k)) = v - h;
   }
 }
 
-// x [B][Cin][HW] -> xt [B][HW][dg * cbs_pg][32]; channel ch of group g sits in block g*cbs_pg + (ch - g*cpg)/32,
+// x [B][Cin][HW] -> xt [B][HW][nb][32]; channel ch of group g sits in block g*cbs_pg + (ch - g*cpg)/32,
 // slot (ch - g*cpg) % 32 (identity when Cin/dg is a multiple of 32; pad slots are zero-filled by the caller).
 // grid (pixel blocks of 32, channel blocks of 64, B), 256 threads.
 __global__ void __launch_bounds__(256) k_dcn_nhwc(const float *__restrict__ x, float *__restrict__ xt,
@@ -97,7 +120,7 @@ __global__ void __launch_bounds__(256) k_dcn_nhwc(const float *__restrict__ x, f
   const long long HW = (long long)s.H * s.W;
   const long long p0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 64, b = blockIdx.z;
-  const int Cp = s.dg * s.cbs_pg * TC_CB;
+  const int Cp = s.nb * TC_CB;
   const int cpg = s.Cin / s.dg;
   {
     const int px = threadIdx.x & 31, cr = threadIdx.x >> 5;
@@ -120,227 +143,281 @@ __global__ void __launch_bounds__(256) k_dcn_nhwc(const float *__restrict__ x, f
   }
 }
 
-// cycle breakdown of CTA (0,0), thread 0 (tools/dbg_dcn_stats.py): total, meta, wait-mma, sample+sync, wait-B, issue, epilogue
-__device__ long long g_dcn_dbg[8];
+// y[b][o][p] = bias[o] + sum_s part[s][b][o][p], s ascending (deterministic split-K epilogue)
+__global__ void __launch_bounds__(256) k_dcn_reduce(const float *__restrict__ part, const float *__restrict__ bias,
+                                                    float *__restrict__ y, int splits, int cout, long long hwo,
+                                                    long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)((i / hwo) % cout);
+    float v = bias ? __ldg(bias + o) : 0.f;
+    for (int s = 0; s < splits; ++s) v += __ldg(part + (long long)s * total + i);
+    y[i] = v;
+  }
+}
 
-template <int CO_T>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+struct ItemTc {
+  int b, cot, b0, b1;     // image, Cout tile, channel blocks [b0, b1)
+  int ty0, tx0, split;
+};
+__device__ __forceinline__ ItemTc tc_item(const DcnShapeTc &s, int item) {
+  ItemTc it;
+  it.split = item % s.splits;
+  int r = item / s.splits;
+  it.cot = r % s.n_cot;
+  r /= s.n_cot;
+  const int tiles = s.tiles_x * s.tiles_y;
+  const int t = r % tiles;
+  it.b = r / tiles;
+  it.ty0 = (t / s.tiles_x) * s.th;
+  it.tx0 = (t % s.tiles_x) * s.tw;
+  it.b0 = (int)((long long)it.split * s.nb / s.splits);
+  it.b1 = (int)((long long)(it.split + 1) * s.nb / s.splits);
+  return it;
+}
+
+template <int CO_T, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset, const float *__restrict__ mask,
                  const float *__restrict__ wtiles, const float *__restrict__ bias, float *__restrict__ y,
-                 const DcnShapeTc s) {
+                 float *__restrict__ part, const DcnShapeTc s) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
-  constexpr int B_BYTES = CO_T * TC_K * 4;
-  unsigned char *a_hi = tc_smem;
-  unsigned char *a_lo = a_hi + TC_A_BYTES;
-  unsigned char *b_hi = a_lo + TC_A_BYTES;
-  unsigned char *b_lo = b_hi + B_BYTES;
-  TapMetaTc *meta = reinterpret_cast<TapMetaTc *>(b_lo + B_BYTES);     // [9][128]
-  __shared__ __align__(8) uint64_t bar_b, bar_mma;
+  constexpr int B_BYTES = CO_T * TC_K * 4;                  // one hi or lo weight tile
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  TapMetaTc *meta = reinterpret_cast<TapMetaTc *>(tc_smem + (size_t)STAGES * STAGE_BYTES);     // [9][128]
+  __shared__ __align__(8) uint64_t a_full[STAGES], b_full[STAGES], empty[STAGES], tm_full[2], tm_empty[2];
   __shared__ uint32_t tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KT = s.kh * s.kw;
   const long long HWo = (long long)s.Ho * s.Wo, HW = (long long)s.H * s.W;
-  const int tiles = (int)((HWo + TC_TP - 1) / TC_TP);
-  const int b = blockIdx.x / tiles;
-  const long long p_base = (long long)(blockIdx.x - b * tiles) * TC_TP;
-  const int cot = blockIdx.y;
-  const int Cp = s.dg * s.cbs_pg * TC_CB;       // channel pitch of the channels-last copy
+  const int Cp = s.nb * TC_CB;       // channel pitch of the channels-last copy
 
   if (tid == 0) {
-    mbar_init(&bar_b, 1);
-    mbar_init(&bar_mma, 1);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&a_full[i], TC_SAMPLERS);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tm_full[i], 1);
+      mbar_init(&tm_empty[i], TC_EPI_WARPS);
+    }
     mbar_fence_init();
   }
-  if (warp == 0) {
+  if (warp == TC_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)),
-                 "n"(CO_T));
+                 "n"(2 * CO_T));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_base;
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO_T >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
 
-  const bool dbg = (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0);
-  long long d_meta = 0, d_wmma = 0, d_samp = 0, d_wb = 0, d_issue = 0, d_epi = 0, tq;
-  const long long d_start = clock64();
-  // sampler geometry: a warp gather covers 4 pixels x 32 channels with lane = pixel * 8 + quad, so each
-  // quarter-warp (the unit the L1 data pipe serves for 16-byte accesses) reads ONE fully used 128-byte
-  // line: 4 wavefronts per gather instead of one per 32-byte sector.  This is what makes the 36x re-read
-  // of the input (9 taps x 4 corners) affordable.  The UMMA tile wants the opposite lane order (a
-  // quarter-warp = 8 rows of one k-chunk, 128 contiguous bytes), so the reduced values are transposed
-  // across the warp with shuffles before the conflict-free 16-byte stores.
-  const int sp = lane >> 3, sq = lane & 7;
-  const float *xbat = xt + (long long)b * HW * Cp + sq * 4;
-  int chunk = 0;
-  for (int g = 0; g < s.dg; ++g) {
-    tq = clock64();
-    // ---- bilinear geometry of every (tap, pixel) of this deformable group (mask folded into the weights)
-    if (chunk > 0) mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));   // (meta is not read by the MMAs, but keep the order simple)
-    __syncthreads();
-    for (int idx = tid; idx < 9 * TC_TP; idx += TC_THREADS) {
-      const int t = idx / TC_TP, pp = idx - t * TC_TP;
-      const long long p = p_base + pp;
-      TapMetaTc mt;
+  if (warp >= TC_WARP_S0) {
+    // =========================================================== samplers: A operand of every chunk
+    const int sw = warp - TC_WARP_S0, st = tid - TC_WARP_S0 * 32;
+    const int sp = lane >> 3, sq = lane & 7;
+    int stage = 0, ph = 0;
+    for (int item = blockIdx.x; item < s.n_items; item += gridDim.x) {
+      const ItemTc it = tc_item(s, item);
+      const float *xbat = xt + (long long)it.b * HW * Cp + sq * 4;
+      int cur_g = -1;
+      for (int bi = it.b0; bi < it.b1; ++bi) {
+        const int g = bi / s.cbs_pg;
+        if (g != cur_g) {
+          // ---- bilinear geometry of every (tap, pixel) of this deformable group (mask folded into the weights)
+          cur_g = g;
+          named_bar_sync(1, TC_SAMPLERS * 32);   // everybody is done reading the previous geometry
+          for (int idx = st; idx < TC_NT * TC_TP; idx += TC_SAMPLERS * 32) {
+            const int t = idx / TC_TP, pp = idx - t * TC_TP;
+            const int ho = it.ty0 + pp / s.tw, wo = it.tx0 + pp % s.tw;
+            TapMetaTc mt;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { mt.o[q] = 0; mt.w[q] = 0.f; }
-      if (p < HWo && t < KT) {
-        const int ho = (int)(p / s.Wo), wo = (int)(p - (long long)ho * s.Wo);
-        const int i = t / s.kw, j = t - i * s.kw;
-        const float *op = offset + ((long long)b * s.dg + g) * 2 * KT * HWo;
-        const float dy = __ldg(op + (2 * t) * HWo + p), dx = __ldg(op + (2 * t + 1) * HWo + p);
-        const float m = __ldg(mask + (((long long)b * s.dg + g) * KT + t) * HWo + p);
-        const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + dy;
-        const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + dx;
-        if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {   // dcn_v2_im2col_cuda.cu:165
-          const float hf = floorf(h_im), wf = floorf(w_im);
-          const int hl = (int)hf, wl = (int)wf;
-          const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-          const int base = hl * s.W + wl;
-          if (hl >= 0 && wl >= 0) { mt.o[0] = base; mt.w[0] = hh * hw * m; }                       // :31-41
-          if (hl >= 0 && wl + 1 <= s.W - 1) { mt.o[1] = base + 1; mt.w[1] = hh * lw * m; }
-          if (hl + 1 <= s.H - 1 && wl >= 0) { mt.o[2] = base + s.W; mt.w[2] = lh * hw * m; }
-          if (hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1) { mt.o[3] = base + s.W + 1; mt.w[3] = lh * lw * m; }
+            for (int q = 0; q < 4; ++q) { mt.o[q] = 0; mt.w[q] = 0.f; }
+            if (ho < s.Ho && wo < s.Wo && t < KT) {
+              const long long p = (long long)ho * s.Wo + wo;
+              const int i = t / s.kw, j = t - i * s.kw;
+              const float *op = offset + ((long long)it.b * s.dg + g) * 2 * KT * HWo;
+              const float dy = __ldg(op + (2 * t) * HWo + p), dx = __ldg(op + (2 * t + 1) * HWo + p);
+              const float m = __ldg(mask + (((long long)it.b * s.dg + g) * KT + t) * HWo + p);
+              const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + dy;
+              const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + dx;
+              if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {   // dcn_v2_im2col_cuda.cu:165
+                const float hf = floorf(h_im), wf = floorf(w_im);
+                const int hl = (int)hf, wl = (int)wf;
+                const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+                const int base = hl * s.W + wl;
+                if (hl >= 0 && wl >= 0) { mt.o[0] = base; mt.w[0] = hh * hw * m; }                       // :31-41
+                if (hl >= 0 && wl + 1 <= s.W - 1) { mt.o[1] = base + 1; mt.w[1] = hh * lw * m; }
+                if (hl + 1 <= s.H - 1 && wl >= 0) { mt.o[2] = base + s.W; mt.w[2] = lh * hw * m; }
+                if (hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1) { mt.o[3] = base + s.W + 1; mt.w[3] = lh * lw * m; }
+              }
+            }
+            meta[idx] = mt;
+          }
+          named_bar_sync(1, TC_SAMPLERS * 32);
+        }
+        const float *xb = xbat + (long long)bi * TC_CB;
+        for (int tap = 0; tap < TC_NT; ++tap) {
+          // warp item = 4 pixels: every lane gathers the 4 corners of its pixel as 16-byte pieces (4 channels);
+          // both of a warp's items (pixels 8w..8w+3 and 8w+4..8w+7) are gathered before either is reduced
+          const int pp0 = sw * 8 + sp, pp1 = pp0 + 4;
+          const TapMetaTc m0 = meta[tap * TC_TP + pp0], m1 = meta[tap * TC_TP + pp1];
+          float4 u0[4], u1[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) u0[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m0.o[q] * Cp));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) u1[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m1.o[q] * Cp));
+          auto reduce = [&](const TapMetaTc &mt, const float4 (&u)[4]) {
+            float4 v;
+            v.x = fmaf(mt.w[3], u[3].x, fmaf(mt.w[2], u[2].x, fmaf(mt.w[1], u[1].x, mt.w[0] * u[0].x)));
+            v.y = fmaf(mt.w[3], u[3].y, fmaf(mt.w[2], u[2].y, fmaf(mt.w[1], u[1].y, mt.w[0] * u[0].y)));
+            v.z = fmaf(mt.w[3], u[3].z, fmaf(mt.w[2], u[2].z, fmaf(mt.w[1], u[1].z, mt.w[0] * u[0].z)));
+            v.w = fmaf(mt.w[3], u[3].w, fmaf(mt.w[2], u[2].w, fmaf(mt.w[1], u[1].w, mt.w[0] * u[0].w)));
+            return v;
+          };
+          const float4 v0 = reduce(m0, u0), v1 = reduce(m1, u1);   // (row sp, quad sq) and (row 4 + sp, quad sq)
+          // the ring slot must have been drained by the MMAs that last read it
+          mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
+          unsigned char *a_hi = tc_smem + (size_t)stage * STAGE_BYTES;
+          unsigned char *a_lo = a_hi + TC_A_BYTES;
+          // transpose: store instruction j writes (row = lane & 7, quad = (lane >> 3) + 4 j); that value lives in
+          // lane (row & 3) * 8 + quad, in v0 for rows 0-3 and v1 for rows 4-7
+          const int row = lane & 7;
+          const bool upper = row >= 4;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int quad = (lane >> 3) + 4 * j;
+            const int src = (row & 3) * 8 + quad;
+            float4 a, c;
+            a.x = __shfl_sync(0xffffffffu, v0.x, src); c.x = __shfl_sync(0xffffffffu, v1.x, src);
+            a.y = __shfl_sync(0xffffffffu, v0.y, src); c.y = __shfl_sync(0xffffffffu, v1.y, src);
+            a.z = __shfl_sync(0xffffffffu, v0.z, src); c.z = __shfl_sync(0xffffffffu, v1.z, src);
+            a.w = __shfl_sync(0xffffffffu, v0.w, src); c.w = __shfl_sync(0xffffffffu, v1.w, src);
+            const float4 v = upper ? c : a;
+            const float4 h4 = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            const uint32_t off = tc_tile_off(sw * 8 + row, quad * 4);
+            *reinterpret_cast<float4 *>(a_hi + off) = h4;
+            *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h4.x, v.y - h4.y, v.z - h4.z, v.w - h4.w);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_tc(&a_full[stage]);
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
       }
-      meta[idx] = mt;
     }
-    __syncthreads();
-    d_meta += clock64() - tq;
-    for (int tg = 0; tg < TC_NTG; ++tg) {     // one tap per chunk
-      for (int cbi = 0; cbi < s.cbs_pg; ++cbi, ++chunk) {
-        tq = clock64();
-        // the previous chunk's MMAs must have consumed A and B before they are overwritten
-        if (chunk > 0) mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));
-        d_wmma += clock64() - tq;
-        tq = clock64();
-        if (tid == 0) {  // B operand (hi + lo tiles, contiguous in the workspace): TMA bulk copies
-          const float *src = wtiles + ((size_t)cot * s.n_chunks + chunk) * 2 * (size_t)CO_T * TC_K;
-          mbar_expect_tx(&bar_b, 2u * B_BYTES);
-          for (uint32_t off = 0; off < 2u * B_BYTES; off += 8192u)
-            bulk_g2s(b_hi + off, reinterpret_cast<const unsigned char *>(src) + off, 8192u, &bar_b);
+  } else if (warp == TC_WARP_TMA) {
+    // =========================================================== B operand: weight tiles by TMA bulk copy
+    if (lane == 0) {
+      int stage = 0, ph = 0;
+      for (int item = blockIdx.x; item < s.n_items; item += gridDim.x) {
+        const ItemTc it = tc_item(s, item);
+        for (int bi = it.b0; bi < it.b1; ++bi) {
+          for (int tap = 0; tap < TC_NT; ++tap) {
+            mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
+            unsigned char *b_hi = tc_smem + (size_t)stage * STAGE_BYTES + 2 * TC_A_BYTES;
+            const float *src = wtiles + (((size_t)it.cot * s.nb + bi) * TC_NT + tap) * 2 * (size_t)CO_T * TC_K;
+            mbar_expect_tx(&b_full[stage], 2u * B_BYTES);
+            for (uint32_t off = 0; off < 2u * B_BYTES; off += 8192u)
+              bulk_g2s(b_hi + off, reinterpret_cast<const unsigned char *>(src) + off, 8192u, &b_full[stage]);
+            if (++stage == STAGES) { stage = 0; ph ^= 1; }
+          }
         }
-        // ---- A operand: sampled column tile of 32 channels of one tap, split into TF32 hi / lo, UMMA layout.
-        //      warp item = 4 pixels: every lane gathers the 4 corners of its pixel as 16-byte pieces
-        //      (4 channels) of the channels-last copy
-        const float *xb = xbat + (long long)(g * s.cbs_pg + cbi) * TC_CB;
-        //      both of a warp's items (pixels 8w..8w+3 and 8w+4..8w+7) are gathered before either is reduced
-        static_assert(TC_TP / 4 == 2 * (TC_THREADS / 32), "two warp items per warp and chunk");
-        const int pp0 = warp * 8 + sp, pp1 = pp0 + 4;
-        const TapMetaTc m0 = meta[tg * TC_TP + pp0], m1 = meta[tg * TC_TP + pp1];
-        float4 u0[4], u1[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) u0[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m0.o[q] * Cp));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) u1[q] = __ldg(reinterpret_cast<const float4 *>(xb + (long long)m1.o[q] * Cp));
-        auto reduce = [&](const TapMetaTc &mt, const float4 (&u)[4]) {
-          float4 v;
-          v.x = fmaf(mt.w[3], u[3].x, fmaf(mt.w[2], u[2].x, fmaf(mt.w[1], u[1].x, mt.w[0] * u[0].x)));
-          v.y = fmaf(mt.w[3], u[3].y, fmaf(mt.w[2], u[2].y, fmaf(mt.w[1], u[1].y, mt.w[0] * u[0].y)));
-          v.z = fmaf(mt.w[3], u[3].z, fmaf(mt.w[2], u[2].z, fmaf(mt.w[1], u[1].z, mt.w[0] * u[0].z)));
-          v.w = fmaf(mt.w[3], u[3].w, fmaf(mt.w[2], u[2].w, fmaf(mt.w[1], u[1].w, mt.w[0] * u[0].w)));
-          return v;
-        };
-        const float4 v0 = reduce(m0, u0), v1 = reduce(m1, u1);   // (row sp, quad sq) and (row 4 + sp, quad sq)
-        // transpose: store instruction j writes (row = lane & 7, quad = (lane >> 3) + 4 j); that value lives in
-        // lane (row & 3) * 8 + quad, in v0 for rows 0-3 and v1 for rows 4-7
-        const int row = lane & 7;
-        const bool upper = row >= 4;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int quad = (lane >> 3) + 4 * j;
-          const int src = (row & 3) * 8 + quad;
-          float4 a, c;
-          a.x = __shfl_sync(0xffffffffu, v0.x, src); c.x = __shfl_sync(0xffffffffu, v1.x, src);
-          a.y = __shfl_sync(0xffffffffu, v0.y, src); c.y = __shfl_sync(0xffffffffu, v1.y, src);
-          a.z = __shfl_sync(0xffffffffu, v0.z, src); c.z = __shfl_sync(0xffffffffu, v1.z, src);
-          a.w = __shfl_sync(0xffffffffu, v0.w, src); c.w = __shfl_sync(0xffffffffu, v1.w, src);
-          const float4 v = upper ? c : a;
-          const float4 h4 = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-          const uint32_t off = tc_tile_off(warp * 8 + row, quad * 4);
-          *reinterpret_cast<float4 *>(a_hi + off) = h4;
-          *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h4.x, v.y - h4.y, v.z - h4.z, v.w - h4.w);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        d_samp += clock64() - tq;
-        if (tid == 0) {
-          tq = clock64();
-          mbar_wait(&bar_b, (uint32_t)(chunk & 1));
-          d_wb += clock64() - tq;
-          tq = clock64();
+      }
+    }
+  } else if (warp == TC_WARP_MMA) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO_T >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
+      int stage = 0, ph = 0, acc = 0, aph = 0;
+      for (int item = blockIdx.x; item < s.n_items; item += gridDim.x) {
+        const ItemTc it = tc_item(s, item);
+        mbar_wait(&tm_empty[acc], (uint32_t)(aph ^ 1));     // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tm + (uint32_t)(acc * CO_T);
+        const int n_ch = (it.b1 - it.b0) * TC_NT;
+        for (int ch = 0; ch < n_ch; ++ch) {
+          mbar_wait(&a_full[stage], (uint32_t)ph);
+          mbar_wait(&b_full[stage], (uint32_t)ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-#pragma unroll 1
+          const uint32_t ah = smem_u32(tc_smem + (size_t)stage * STAGE_BYTES), al = ah + TC_A_BYTES;
+          const uint32_t bh = al + TC_A_BYTES, bl = bh + B_BYTES;
+#pragma unroll
           for (int ks = 0; ks < TC_K / 8; ++ks) {   // one UMMA per 8 k (two 16-byte k-chunks), 3 per step (3xTF32)
             const uint32_t koff = (uint32_t)ks * 2u * TC_LBO;
             const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
             const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
-            const uint32_t acc0 = (chunk > 0 || ks > 0) ? 1u : 0u;
+            const uint32_t acc0 = (ch > 0 || ks > 0) ? 1u : 0u;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dal), "l"(dbh),
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(dal), "l"(dbh),
                          "r"(idesc), "r"(acc0) : "memory");      // lo * hi   (small terms first)
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbl),
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(dah), "l"(dbl),
                          "r"(idesc), "r"(1u) : "memory");        // hi * lo
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(dah), "l"(dbh),
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(dah), "l"(dbh),
                          "r"(idesc), "r"(1u) : "memory");        // hi * hi
           }
+          // frees the ring slot (A and B) once the MMAs above have read it
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                           smem_u32(&bar_mma)) : "memory");
-          d_issue += clock64() - tq;
+                           smem_u32(&empty[stage])) : "memory");
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&tm_full[acc])) : "memory");
+        if (++acc == 2) { acc = 0; aph ^= 1; }
       }
     }
-  }
-  // ---- epilogue: TMEM -> registers -> bias -> global (coalesced along pixels)
-  tq = clock64();
-  mbar_wait(&bar_mma, (uint32_t)((chunk - 1) & 1));
-  d_wmma += clock64() - tq;
-  tq = clock64();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (warp < 8) {
-    constexpr int HALF = CO_T / 2;                 // columns per warp group (warps 0-3: first half, 4-7: second)
-    const int q = warp & 3, h = warp >> 2;
-    const long long p = p_base + q * 32 + lane;
-    const uint32_t taddr = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HALF);
+  } else {
+    // =========================================================== epilogue: TMEM -> registers -> bias -> global
+    const int q = warp;                 // TMEM lane quarter == warp index (warps 0..3)
+    int acc = 0, aph = 0;
+    for (int item = blockIdx.x; item < s.n_items; item += gridDim.x) {
+      const ItemTc it = tc_item(s, item);
+      const int pp = q * 32 + lane;
+      const int ho = it.ty0 + pp / s.tw, wo = it.tx0 + pp % s.tw;
+      const bool ok = ho < s.Ho && wo < s.Wo;
+      const long long p = (long long)ho * s.Wo + wo;
+      float *dst = (s.splits > 1 ? part + (long long)it.split * s.B * s.Cout * HWo : y) + (long long)it.b * s.Cout * HWo + p;
+      mbar_wait(&tm_full[acc], (uint32_t)aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CO_T);
 #pragma unroll 1
-    for (int c32 = 0; c32 < HALF; c32 += 32) {
-      uint32_t v[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
-          "%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr + (uint32_t)c32));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (p < HWo) {
+      for (int c32 = 0; c32 < CO_T; c32 += 32) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+            "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + (uint32_t)c32));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int o = cot * CO_T + h * HALF + c32 + j;
-          if (o < s.Cout) {
-            const float bv = bias ? __ldg(bias + o) : 0.f;
-            y[((long long)b * s.Cout + o) * HWo + p] = __uint_as_float(v[j]) + bv;
+          for (int j = 0; j < 32; ++j) {
+            const int o = it.cot * CO_T + c32 + j;
+            if (o < s.Cout) {
+              const float bv = (bias && s.splits == 1) ? __ldg(bias + o) : 0.f;
+              dst[(long long)o * HWo] = __uint_as_float(v[j]) + bv;
+            }
           }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_tc(&tm_empty[acc]);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  d_epi = clock64() - tq;
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(CO_T));
-  if (dbg) {
-    g_dcn_dbg[0] = clock64() - d_start; g_dcn_dbg[1] = d_meta; g_dcn_dbg[2] = d_wmma; g_dcn_dbg[3] = d_samp;
-    g_dcn_dbg[4] = d_wb; g_dcn_dbg[5] = d_issue; g_dcn_dbg[6] = d_epi; g_dcn_dbg[7] = chunk;
-  }
+  if (warp == TC_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(2 * CO_T));
 }
 
 static void fill_shape(DcnShapeTc *s, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph,
@@ -350,60 +427,122 @@ static void fill_shape(DcnShapeTc *s, int b, int cin, int h, int w, int cout, in
   s->Ho = (h + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
   s->Wo = (w + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
   s->co_t = cout > 64 ? 128 : 64;
+  s->n_cot = (cout + s->co_t - 1) / s->co_t;
   const int cpg = cin / dg;
   s->cbs_pg = (cpg + TC_CB - 1) / TC_CB;
-  s->n_chunks = dg * TC_NTG * s->cbs_pg;
-}
-
-static size_t tc_weight_bytes(const DcnShapeTc &s) {
-  const int cot = (s.Cout + s.co_t - 1) / s.co_t;
-  return align_up((size_t)cot * s.n_chunks * 2 * s.co_t * TC_K * 4, 256);
-}
-
-// weights re-tiled (hi/lo) + the channels-last copy of the input
-size_t dcn_tc_workspace_bytes(int b, int cin, int h, int w, int cout, int dg) {
-  DcnShapeTc s;
-  fill_shape(&s, b, cin, h, w, cout, 3, 3, 1, 1, 1, 1, 1, 1, dg);
-  return tc_weight_bytes(s) + align_up((size_t)b * h * w * dg * s.cbs_pg * TC_CB * 4, 256);
-}
-
-// Tensor-core forward.  Requires kh*kw <= 9 (checked by the caller) and a workspace of
-// dcn_tc_workspace_bytes(); enqueues the weight re-tiling, the channels-last copy and the fused forward.
-int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
-                   const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
-                   int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream) {
-  DcnShapeTc s;
-  fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
-  const int cot = (cout + s.co_t - 1) / s.co_t;
-  float *ws = reinterpret_cast<float *>(workspace);
-  float *xt = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + tc_weight_bytes(s));
-  k_dcn_prep_weights<<<cot * s.n_chunks, 256, 0, stream>>>(weight, s, ws);
-  CNB_CHECK_LAUNCH("cnb_dcnv2_forward weight tiles");
-  const long long HW = (long long)h * w;
-  if ((cin / dg) % TC_CB != 0)   // pad slots of the last channel block of every group must read as zero
-    CNB_CUDA(cudaMemsetAsync(xt, 0, (size_t)b * HW * dg * s.cbs_pg * TC_CB * 4, stream));
-  dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((cin + 63) / 64), (unsigned)b);
-  k_dcn_nhwc<<<tgrid, 256, 0, stream>>>(input, xt, s);
-  CNB_CHECK_LAUNCH("cnb_dcnv2_forward channels-last copy");
-  const long long HWo = (long long)s.Ho * s.Wo;
-  const int tiles = (int)((HWo + TC_TP - 1) / TC_TP);
-  dim3 grid((unsigned)(b * tiles), (unsigned)cot);
-  const size_t smem = 2 * (size_t)TC_A_BYTES + 2 * (size_t)s.co_t * TC_K * 4 + sizeof(TapMetaTc) * 9 * TC_TP;
-  if (s.co_t == 64) {
-    CNB_CUDA(cudaFuncSetAttribute(k_dcn_forward_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dcn_forward_tc<64><<<grid, TC_THREADS, smem, stream>>>(xt, offset, mask, ws, bias, output, s);
-  } else {
-    CNB_CUDA(cudaFuncSetAttribute(k_dcn_forward_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dcn_forward_tc<128><<<grid, TC_THREADS, smem, stream>>>(xt, offset, mask, ws, bias, output, s);
+  s->nb = dg * s->cbs_pg;
+  s->tw = s->Wo >= 12 ? 16 : 8;          // 8 x 16 pixel tiles; 16 x 8 on narrow maps
+  s->th = TC_TP / s->tw;
+  s->tiles_x = (s->Wo + s->tw - 1) / s->tw;
+  s->tiles_y = (s->Ho + s->th - 1) / s->th;
+  const long long base_items = (long long)b * s->tiles_x * s->tiles_y * s->n_cot;
+  int splits = 1;
+  const int sms = num_sms();
+  if (base_items < sms) {                 // small maps: split the channel blocks so every SM gets an item
+    splits = (int)((sms + base_items - 1) / base_items);
+    if (splits > s->nb) splits = s->nb;
+    if (splits > 8) splits = 8;
+    if (splits < 1) splits = 1;
   }
-  CNB_CHECK_LAUNCH("cnb_dcnv2_forward (tcgen05)");
-  count_launch(3);
+  s->splits = splits;
+  s->n_items = (int)(base_items * splits);
+}
+
+size_t dcn_tc_wtiles_bytes(int cin, int cout, int dg) {
+  DcnShapeTc s;
+  fill_shape(&s, 1, cin, 8, 8, cout, 3, 3, 1, 1, 1, 1, 1, 1, dg);
+  return align_up((size_t)s.n_cot * s.nb * TC_NT * 2 * s.co_t * TC_K * 4, 256);
+}
+static size_t tc_xt_bytes(const DcnShapeTc &s) { return align_up((size_t)s.B * s.H * s.W * s.nb * TC_CB * 4, 256); }
+static size_t tc_part_bytes(const DcnShapeTc &s) {
+  return s.splits > 1 ? align_up((size_t)s.splits * s.B * s.Cout * s.Ho * s.Wo * 4, 256) : 0;
+}
+
+// workspace of the prepared forward: channels-last copy of the input (+ split-K partial sums)
+size_t dcn_tc_fwd_workspace_bytes(int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int ph, int dh, int dg) {
+  DcnShapeTc s;
+  fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sh, ph, ph, dh, dh, dg);
+  return tc_xt_bytes(s) + tc_part_bytes(s);
+}
+// workspace of the plain forward: weight tiles + the above
+size_t dcn_tc_workspace_bytes(int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int ph, int dh, int dg) {
+  return dcn_tc_wtiles_bytes(cin, cout, dg) + dcn_tc_fwd_workspace_bytes(b, cin, h, w, cout, kh, kw, sh, ph, dh, dg);
+}
+
+int dcn_prepare_weights_tc(const float *weight, int cin, int cout, int kh, int kw, int dg, float *wtiles,
+                           cudaStream_t stream) {
+  DcnShapeTc s;
+  fill_shape(&s, 1, cin, 8, 8, cout, kh, kw, 1, 1, 1, 1, 1, 1, dg);
+  k_dcn_prep_weights<<<s.n_cot * s.nb * TC_NT, 256, 0, stream>>>(weight, s, wtiles);
+  CNB_CHECK_LAUNCH("cnb_dcnv2 weight tiles");
+  count_launch();
   return CNB_OK;
 }
 
-}  // namespace cnb
-
-// debug: cycle breakdown of the last tensor-core forward (CTA 0, thread 0); synchronises the device
-extern "C" int cnb_debug_dcn_stats(long long *out8) {
-  return cudaMemcpyFromSymbol(out8, cnb::g_dcn_dbg, sizeof(long long) * 8) == cudaSuccess ? 0 : 1;
+template <int CO_T, int STAGES>
+static int launch_fwd(const float *xt, const float *offset, const float *mask, const float *wtiles, const float *bias,
+                      float *output, float *part, const DcnShapeTc &s, cudaStream_t stream) {
+  const size_t smem = (size_t)STAGES * (2 * TC_A_BYTES + 2 * CO_T * TC_K * 4) + sizeof(TapMetaTc) * TC_NT * TC_TP;
+  static thread_local int dev_done = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev_done != dev) {
+    CNB_CUDA(cudaFuncSetAttribute(k_dcn_forward_tc<CO_T, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dev_done = dev;
+  }
+  const int grid = s.n_items < num_sms() ? s.n_items : num_sms();
+  k_dcn_forward_tc<CO_T, STAGES><<<grid, TC_THREADS, smem, stream>>>(xt, offset, mask, wtiles, bias, output, part, s);
+  CNB_CHECK_LAUNCH("cnb_dcnv2_forward (tcgen05)");
+  count_launch();
+  return CNB_OK;
 }
+
+// Tensor-core forward from pre-tiled weights.  input_nhwc != 0: `input` already is [B][H*W][Cin] (torch
+// channels_last) and Cin/dg is a multiple of 32 -- no re-layout pass.  Requires kh*kw <= 9 (checked by the caller).
+int dcn_forward_tc_prepared(const float *input, int input_nhwc, const float *offset, const float *mask,
+                            const float *wtiles, const float *bias, float *output, int b, int cin, int h, int w,
+                            int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
+                            void *workspace, cudaStream_t stream) {
+  DcnShapeTc s;
+  fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
+  float *xt = reinterpret_cast<float *>(workspace);
+  float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + tc_xt_bytes(s));
+  const long long HW = (long long)h * w;
+  const float *xsrc = xt;
+  if (input_nhwc && (cin / dg) % TC_CB == 0) {
+    xsrc = input;
+  } else {
+    if ((cin / dg) % TC_CB != 0)   // pad slots of the last channel block of every group must read as zero
+      CNB_CUDA(cudaMemsetAsync(xt, 0, (size_t)b * HW * s.nb * TC_CB * 4, stream));
+    dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((cin + 63) / 64), (unsigned)b);
+    k_dcn_nhwc<<<tgrid, 256, 0, stream>>>(input, xt, s);
+    CNB_CHECK_LAUNCH("cnb_dcnv2_forward channels-last copy");
+    count_launch();
+  }
+  int rc;
+  if (s.co_t == 64) rc = launch_fwd<64, 3>(xsrc, offset, mask, wtiles, bias, output, part, s, stream);
+  else rc = launch_fwd<128, 2>(xsrc, offset, mask, wtiles, bias, output, part, s, stream);
+  if (rc != CNB_OK) return rc;
+  if (s.splits > 1) {
+    const long long total = (long long)b * cout * s.Ho * s.Wo;
+    const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    k_dcn_reduce<<<grid, 256, 0, stream>>>(part, bias, output, s.splits, cout, (long long)s.Ho * s.Wo, total);
+    CNB_CHECK_LAUNCH("cnb_dcnv2_forward split-K reduce");
+    count_launch();
+  }
+  return CNB_OK;
+}
+
+// Plain forward: tiles the weights into the head of the workspace, then the prepared forward.
+int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
+                   const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
+                   int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream) {
+  float *wt = reinterpret_cast<float *>(workspace);
+  int rc = dcn_prepare_weights_tc(weight, cin, cout, kh, kw, dg, wt, stream);
+  if (rc != CNB_OK) return rc;
+  return dcn_forward_tc_prepared(input, 0, offset, mask, wt, bias, output, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw,
+                                 dh, dw, dg, reinterpret_cast<char *>(workspace) + dcn_tc_wtiles_bytes(cin, cout, dg),
+                                 stream);
+}
+
+}  // namespace cnb

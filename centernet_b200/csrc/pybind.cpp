@@ -160,6 +160,21 @@ PYBIND11_MODULE(_C, m) {
                             kh, kw, sh, sw, ph, pw, dh, dw, dg, ptr<void>(ws), wsb, ptr<void>(stream)),
           "cnb_dcnv2_forward");
   });
+  m.def("dcnv2_wtiles_bytes", &cnb_dcnv2_wtiles_bytes);
+  m.def("dcnv2_prepare_weights", [](P weight, int cin, int cout, int kh, int kw, int dg, P wt, size_t wtb, P stream) {
+    check(cnb_dcnv2_prepare_weights(ptr<const float>(weight), cin, cout, kh, kw, dg, ptr<void>(wt), wtb,
+                                    ptr<void>(stream)),
+          "cnb_dcnv2_prepare_weights");
+  });
+  m.def("dcnv2_prepared_workspace_bytes", &cnb_dcnv2_prepared_workspace_bytes);
+  m.def("dcnv2_forward_prepared", [](P input, int nhwc, P offset, P mask, P wt, P bias, P output, int b, int cin, int h,
+                                     int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                                     int dg, P ws, size_t wsb, P stream) {
+    check(cnb_dcnv2_forward_prepared(ptr<const float>(input), nhwc, ptr<const float>(offset), ptr<const float>(mask),
+                                     ptr<const void>(wt), ptr<const float>(bias), ptr<float>(output), b, cin, h, w,
+                                     cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, ptr<void>(ws), wsb, ptr<void>(stream)),
+          "cnb_dcnv2_forward_prepared");
+  });
   m.def("dcnv2_backward", [](P input, P offset, P mask, P weight, P gout, P gin, P goff, P gmask, P gw, P gb, int b,
                              int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
                              int dw, int dg, P ws, size_t wsb, P stream) {

@@ -321,70 +321,10 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
   G::sync();
 }
 
-// Merge the segments of image b (written by the stage-1 CTAs i0..i1), sort, emit.
-// sbuf must hold next_pow2(max(max_slots*K, K)) keys.  All threads of the CTA call.
-__device__ long long g_fin_t[4];
-template <bool NMS, typename G>
-__device__ void finalize_image(const float *__restrict__ src, const SelectPlan &pl, int b,
-                               const u64 *__restrict__ cand, const int *__restrict__ cand_cnt,
-                               const FinalizeOut &out, u64 *sbuf, int *s_tmp, u64 *s_red,
-                               const uint32_t *cand_thr = nullptr) {
+// Write the K rows of image b from its sorted keys (raw top-K outputs and/or the fused ctdet epilogue).
+template <typename G>
+__device__ __forceinline__ void emit_rows(const SelectPlan &pl, int b, const u64 *sbuf, const FinalizeOut &out) {
   const int tid = G::tid(), K = pl.K;
-  if (tid == 0) {  // the binary search costs ~1k instructions: one thread does it
-    s_tmp[30] = plan_cta_of_plane(pl, (long long)b * pl.C);
-    s_tmp[31] = plan_cta_of_plane(pl, (long long)(b + 1) * pl.C - 1);
-  }
-  G::sync();
-  const int i0 = s_tmp[30], i1 = s_tmp[31];
-  int total = 0;
-  long long tq0 = clock64();
-  for (int slot = 0; slot <= i1 - i0; ++slot) {
-    const int n = __ldcg(cand_cnt + (size_t)b * pl.max_slots + slot);
-    const u64 *seg = cand + ((size_t)b * pl.max_slots + slot) * pl.seg_cap;
-    for (int t = tid; t < n; t += G::n()) sbuf[total + t] = __ldcg(seg + t);
-    total += n;
-  }
-  G::sync();
-  long long tq1 = clock64();
-  if (cand_thr != nullptr && total > 2 * K && total <= 2 * G::n()) {
-    // every segment comes with a valid lower bound of the image's K-th best score (the K-th best of
-    // a subset never exceeds the K-th best of the whole), so the largest of them is one too: drop
-    // everything below it before sorting (>= K survive, usually ~1.2 K; <= 2 keys per thread here)
-    uint32_t tb = 0u;
-    for (int slot = 0; slot <= i1 - i0; ++slot) tb = max(tb, __ldcg(cand_thr + (size_t)b * pl.max_slots + slot));
-    if (tid == 0) s_tmp[0] = 0;
-    const u64 mine0 = (tid < total) ? sbuf[tid] : 0ull;
-    const u64 mine1 = (tid + G::n() < total) ? sbuf[tid + G::n()] : 0ull;
-    G::sync();
-    if (mine0 != 0ull && key_bits(mine0) >= tb) sbuf[atomicAdd(&s_tmp[0], 1)] = mine0;
-    if (mine1 != 0ull && key_bits(mine1) >= tb) sbuf[atomicAdd(&s_tmp[0], 1)] = mine1;
-    G::sync();
-    total = s_tmp[0];
-    G::sync();
-  }
-  if (total <= 256 && total <= G::n() && G::n() >= 256) {
-    // few survivors: rank sort (every key counts the keys above it; no dependent network stages)
-    const u64 mine = (tid < total) ? sbuf[tid] : 0ull;
-    int rank = 0;
-    if (tid < total)
-      for (int t = 0; t < total; ++t) rank += (sbuf[t] > mine) ? 1 : 0;
-    G::sync();
-    const int n2 = max(total, K);
-    for (int t = total + tid; t < n2; t += G::n()) sbuf[t] = 0ull;
-    if (tid < total) sbuf[rank] = mine;
-    G::sync();
-  } else {
-    const int n = next_pow2(max(total, K));
-    for (int t = total + tid; t < n; t += G::n()) sbuf[t] = 0ull;
-    G::sync();
-    sort_desc_best<G>(sbuf, n);  // segments may be unsorted supersets (hot kernel)
-  }
-  const int n = next_pow2(max(total, K));
-  long long tq2 = clock64();
-  if (total < K) {
-    const long long N = (long long)pl.C * pl.H * pl.W;
-    finalize_fill<NMS, G>(src + (long long)b * N, pl, sbuf, total, K, s_tmp, s_red);
-  }
   const long long HW = (long long)pl.H * pl.W;
   for (int k = tid; k < K; k += G::n()) {
     const u64 key = sbuf[k];
@@ -421,13 +361,69 @@ __device__ void finalize_image(const float *__restrict__ src, const SelectPlan &
       d[5] = (float)cls;
     }
   }
-  G::sync();
-  if (pl.dbg && tid == 0 && b == 5) {
-    pl.dbg[148 * 8 + 0] = (unsigned long long)(tq1 - tq0);
-    pl.dbg[148 * 8 + 1] = (unsigned long long)(tq2 - tq1);
-    pl.dbg[148 * 8 + 2] = (unsigned long long)(clock64() - tq2);
-    pl.dbg[148 * 8 + 3] = (unsigned long long)n;
+}
+
+// Merge the segments of image b (written by the stage-1 CTAs i0..i1), sort, emit.
+// sbuf must hold next_pow2(max(max_slots*K, K)) keys.  All threads of the CTA call.
+template <bool NMS, typename G>
+__device__ void finalize_image(const float *__restrict__ src, const SelectPlan &pl, int b,
+                               const u64 *__restrict__ cand, const int *__restrict__ cand_cnt,
+                               const FinalizeOut &out, u64 *sbuf, int *s_tmp, u64 *s_red,
+                               const uint32_t *cand_thr = nullptr) {
+  const int tid = G::tid(), K = pl.K;
+  if (tid == 0) {  // the binary search costs ~1k instructions: one thread does it
+    s_tmp[30] = plan_cta_of_plane(pl, (long long)b * pl.C);
+    s_tmp[31] = plan_cta_of_plane(pl, (long long)(b + 1) * pl.C - 1);
   }
+  G::sync();
+  const int i0 = s_tmp[30], i1 = s_tmp[31];
+  int total = 0;
+  for (int slot = 0; slot <= i1 - i0; ++slot) {
+    const int n = __ldcg(cand_cnt + (size_t)b * pl.max_slots + slot);
+    const u64 *seg = cand + ((size_t)b * pl.max_slots + slot) * pl.seg_cap;
+    for (int t = tid; t < n; t += G::n()) sbuf[total + t] = __ldcg(seg + t);
+    total += n;
+  }
+  G::sync();
+  if (cand_thr != nullptr && total > 2 * K && total <= 2 * G::n()) {
+    // every segment comes with a valid lower bound of the image's K-th best score (the K-th best of
+    // a subset never exceeds the K-th best of the whole), so the largest of them is one too: drop
+    // everything below it before sorting (>= K survive, usually ~1.2 K; <= 2 keys per thread here)
+    uint32_t tb = 0u;
+    for (int slot = 0; slot <= i1 - i0; ++slot) tb = max(tb, __ldcg(cand_thr + (size_t)b * pl.max_slots + slot));
+    if (tid == 0) s_tmp[0] = 0;
+    const u64 mine0 = (tid < total) ? sbuf[tid] : 0ull;
+    const u64 mine1 = (tid + G::n() < total) ? sbuf[tid + G::n()] : 0ull;
+    G::sync();
+    if (mine0 != 0ull && key_bits(mine0) >= tb) sbuf[atomicAdd(&s_tmp[0], 1)] = mine0;
+    if (mine1 != 0ull && key_bits(mine1) >= tb) sbuf[atomicAdd(&s_tmp[0], 1)] = mine1;
+    G::sync();
+    total = s_tmp[0];
+    G::sync();
+  }
+  if (total <= 256 && total <= G::n() && G::n() >= 256) {
+    // few survivors: rank sort (every key counts the keys above it; no dependent network stages)
+    const u64 mine = (tid < total) ? sbuf[tid] : 0ull;
+    int rank = 0;
+    if (tid < total)
+      for (int t = 0; t < total; ++t) rank += (sbuf[t] > mine) ? 1 : 0;
+    G::sync();
+    const int n2 = max(total, K);
+    for (int t = total + tid; t < n2; t += G::n()) sbuf[t] = 0ull;
+    if (tid < total) sbuf[rank] = mine;
+    G::sync();
+  } else {
+    const int n = next_pow2(max(total, K));
+    for (int t = total + tid; t < n; t += G::n()) sbuf[t] = 0ull;
+    G::sync();
+    sort_desc_best<G>(sbuf, n);  // segments may be unsorted supersets (hot kernel)
+  }
+  if (total < K) {
+    const long long N = (long long)pl.C * pl.H * pl.W;
+    finalize_fill<NMS, G>(src + (long long)b * N, pl, sbuf, total, K, s_tmp, s_red);
+  }
+  emit_rows<G>(pl, b, sbuf, out);
+  G::sync();
 }
 
 // ------------------------------------------------------------------ stage 1
@@ -780,20 +776,141 @@ k_select_stage1(const float *__restrict__ src, const SelectPlan pl, u64 *__restr
 }
 
 // ------------------------------------------------------------------ stage 1, hot geometry, warp-asynchronous
-// Whole 128x128 planes, TMA, NMS, fused finalize.  Within an image there is NO CTA-wide barrier:
+// Whole 128x128 planes, TMA, NMS, fused finalize, any batch size.  Within an image there is NO CTA-wide
+// barrier:
 //   * every warp waits for the plane (mbarrier), sweeps its 4 rows (phase A) and pushes its own
 //     qualifying pixels straight from registers into the shared key buffer + histogram (atomics;
-//     ~20-100 pushes per plane in steady state), then arrives on sdone[stage];
-//   * warp (u mod 32) additionally refreshes the histogram threshold and, once all 32 warps have
-//     arrived for unit u, re-arms the stage with the TMA load of unit u+3.
+//     ~20-100 pushes per plane in steady state), then arrives on s_arr[stage];
+//   * warp (u mod 32) additionally refreshes the histogram threshold and the LAST warp to finish unit u
+//     re-arms the stage with the TMA load of unit u+3.
 // Warps therefore drift apart by up to the depth of the stage ring and hide each other's latencies.
-// CTA barriers exist only at image boundaries (<= 2 per CTA at B=64): flush + ticket + finalize are
-// CTA-parallel there, and the first unit of an image is bootstrapped in two steps (16 rows first)
-// so a threshold exists before the bulk of the plane is pushed.  If the key buffer ever overflows
-// (plateaus, very dense peaks) the CTA re-derives its segment of that image exactly from global
-// memory at flush time (slow path, sort-prune).
+// CTA barriers exist only at image boundaries:
+//   * bootstrap of the first plane of an image: pass 1 sweeps the plane WITHOUT a threshold and only
+//     histograms its ~1.8 k peaks (one spread shared-memory atomic each, no key stores); the K-th best of
+//     the plane becomes the threshold; pass 2 sweeps the (still resident) plane again and pushes the
+//     ~1.0-1.3 K keys above it.  Two register-only sweeps instead of ~750 three-atomic pushes.
+//   * flush: the buffer is cut against the final threshold and delivered UNSORTED (<= seg_cap keys) with
+//     that threshold; the last CTA to deliver an image (atomic ticket) finalizes it.  An image that lies
+//     entirely inside one CTA skips the global round trip and is finalized straight from shared memory
+//     (_topk_channel planes, C = 1).
+//   * finalize (finalize_hot): counts, thresholds and keys of all segments are fetched in ONE round of
+//     independent L2 loads, cut with the largest segment threshold (a valid lower bound of the K-th
+//     best), rank-sorted by 4 threads per key and emitted with the ctdet gathers fused.
+// If the key buffer ever overflows (plateaus, very dense peaks) the CTA re-derives its segment of that
+// image exactly from global memory at flush time (slow path, sort-prune).
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+enum { SW_BOTH = 0, SW_HIST = 1, SW_KEYS = 2 };  // what a qualifying pixel updates: histogram and/or key buffer
+
+// Finalize image b inside the hot kernel (all SEL_THREADS threads).  `local`: the keys are already in
+// sbuf[0..n_local) (image owned by this CTA alone); otherwise they are merged from the `nslots` segments.
+// sbuf holds SEL_CAP keys; s_fcnt holds >= nslots ints.
+__device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl, int b, int nslots, bool local,
+                             int n_local, const u64 *__restrict__ cand, const int *__restrict__ cand_cnt,
+                             const uint32_t *__restrict__ cand_thr, const FinalizeOut &out, u64 *sbuf, int *s_fcnt,
+                             int *s_tmp, u64 *s_red) {
+  const int tid = threadIdx.x, K = pl.K, cap = pl.seg_cap;
+  int total;
+  bool sorted = false;
+  if (local) {
+    total = n_local;
+  } else {
+    const size_t base = (size_t)b * pl.max_slots;
+    const u64 *keys = cand + base * (size_t)cap;   // the segments of one image are contiguous
+    const int items = nslots * cap;
+    // speculative key loads (independent of the counts, so counts + thresholds + keys cost ONE L2 round
+    // trip; slots beyond a segment's count hold stale workspace bytes that are never used)
+    u64 k0 = 0ull, k1 = 0ull;
+    if (tid < items) k0 = __ldcg(keys + tid);
+    if (tid + SEL_THREADS < items) k1 = __ldcg(keys + tid + SEL_THREADS);
+    if (tid == 0) { s_tmp[0] = 0; s_tmp[1] = 0; s_tmp[2] = 0; }
+    __syncthreads();
+    for (int s = tid; s < nslots; s += SEL_THREADS) {
+      s_fcnt[s] = __ldcg(cand_cnt + base + s);
+      atomicMax(reinterpret_cast<unsigned int *>(&s_tmp[1]), __ldcg(cand_thr + base + s));
+    }
+    __syncthreads();
+    // every segment threshold is a valid lower bound of the image's K-th best score (the K-th best of a
+    // subset never exceeds the K-th best of the whole), hence so is the largest of them
+    const uint32_t T = (uint32_t)s_tmp[1];
+    auto take = [&](u64 key, int it) {
+      const int slot = it / cap, j = it - slot * cap;
+      if (j < s_fcnt[slot] && key_bits(key) >= T) {
+        const int pos = atomicAdd(&s_tmp[0], 1);
+        if (pos < SEL_CAP) sbuf[pos] = key;
+        else s_tmp[2] = 1;
+      }
+    };
+    if (tid < items) take(k0, tid);
+    if (tid + SEL_THREADS < items) take(k1, tid + SEL_THREADS);
+    for (int it0 = 2 * SEL_THREADS; it0 < items; it0 += 4 * SEL_THREADS) {   // small batches: many slots
+      u64 kk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int it = it0 + q * SEL_THREADS + tid;
+        kk[q] = (it < items) ? __ldcg(keys + it) : 0ull;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int it = it0 + q * SEL_THREADS + tid;
+        if (it < items) take(kk[q], it);
+      }
+    }
+    __syncthreads();
+    total = s_tmp[0];
+    if (s_tmp[2]) {
+      // more than SEL_CAP keys above the cut (plateaus spanning many segments): exact chunked sort-prune
+      __syncthreads();
+      if (tid == 0) s_tmp[0] = 0;
+      __syncthreads();
+      u64 thr64 = 0ull;
+      const int per = max(1, (SEL_CAP / 2) / cap);   // slots per step: <= CAP/2 new keys + <= K kept
+      for (int s0 = 0; s0 < nslots; s0 += per) {
+        const int s1 = min(nslots, s0 + per);
+        for (int it = s0 * cap + tid; it < s1 * cap; it += SEL_THREADS) {
+          const int slot = it / cap, j = it - slot * cap;
+          if (j < s_fcnt[slot]) {
+            const u64 key = __ldcg(keys + it);
+            if (key > thr64) sbuf[atomicAdd(&s_tmp[0], 1)] = key;
+          }
+        }
+        thr64 = cta_prune(sbuf, &s_tmp[0], K);
+      }
+      total = min(s_tmp[0], K);
+      sorted = true;
+    }
+  }
+  const u64 *res = sbuf;
+  if (!sorted) {
+    if (total <= 256) {
+      // few survivors: rank sort, 4 threads per key (every key counts the keys above it; keys are unique)
+      u64 *dst = sbuf + SEL_CAP / 2;
+      const int q = tid >> 2, part = tid & 3;
+      const u64 mine = (q < total) ? sbuf[q] : 0ull;
+      int rank = 0;
+      if (q < total)
+        for (int t = part; t < total; t += 4) rank += (sbuf[t] > mine) ? 1 : 0;
+      rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+      rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+      for (int t = total + tid; t < max(total, K); t += SEL_THREADS) dst[t] = 0ull;
+      if (q < total && part == 0) dst[rank] = mine;
+      __syncthreads();
+      res = dst;
+    } else {
+      const int n = next_pow2(max(total, K));
+      for (int t = total + tid; t < n; t += SEL_THREADS) sbuf[t] = 0ull;
+      __syncthreads();
+      cta_sort_desc(sbuf, n);
+    }
+  }
+  if (total < K) {
+    const long long N = (long long)pl.C * pl.H * pl.W;
+    finalize_fill<true, CtaGroup>(src + (long long)b * N, pl, const_cast<u64 *>(res), total, K, s_tmp, s_red);
+  }
+  emit_rows<CtaGroup>(pl, b, res, out);
+  __syncthreads();
 }
 
 template <bool LOGITS>
@@ -805,8 +922,8 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   u64 *buf = reinterpret_cast<u64 *>(smem_raw + (size_t)SEL_STAGES * SEL_STAGE_BYTES);
   int *fine = reinterpret_cast<int *>(buf + SEL_CAP);
   int *coarse = fine + SEL_HIST_FINE;
-  uint32_t *unused_masks = reinterpret_cast<uint32_t *>(coarse + SEL_HIST_COARSE);
-  uint64_t *full = reinterpret_cast<uint64_t *>(unused_masks + SEL_MASK_WORDS);
+  int *s_fcnt = reinterpret_cast<int *>(coarse + SEL_HIST_COARSE);   // SEL_MASK_WORDS (512) ints >= SEL_MAX_CTA
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_fcnt + SEL_MASK_WORDS);
   int *s_cnt = reinterpret_cast<int *>(full + SEL_STAGES);   // [0] count [1] overflow [2] last flag [3] compaction
   uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_cnt + 4);
   float *s_tl = reinterpret_cast<float *>(s_cnt + 5);        // LOGITS: logit-space lower bound of *s_thr
@@ -814,12 +931,15 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   __shared__ int s_flag[4];                                  // compaction rendezvous requested for unit (u & 3)
   __shared__ int s_tmp[32];
   __shared__ u64 s_red[32];
+  static_assert(SEL_MASK_WORDS >= SEL_MAX_CTA, "s_fcnt must hold one count per candidate segment");
+  static_assert(SEL_HIST_FINE == 64 * SEL_WARPS, "bootstrap derives one coarse bin per warp");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = pl.K, C = pl.C;
   constexpr int HW = 128 * 128;
-  const long long p_begin = plan_first_plane(pl, blockIdx.x);
-  const long long p_end = plan_first_plane(pl, blockIdx.x + 1);
+  const int me = (int)blockIdx.x;
+  const long long p_begin = plan_first_plane(pl, me);
+  const long long p_end = plan_first_plane(pl, me + 1);
   const int total_units = (int)(p_end - p_begin);
   const float NI = CNB_NEG_INF;
 
@@ -832,13 +952,13 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     for (uint32_t off = 0; off < (uint32_t)SEL_STAGE_BYTES; off += 16384u)
       bulk_g2s(dst + off, gsrc + off, 16384u, &full[s]);
   };
-  auto reset_state = [&]() {  // all threads, followed by a barrier at the call site
+  auto clear_hist = [&]() {
     for (int i = tid; i < SEL_HIST_FINE + SEL_HIST_COARSE; i += SEL_THREADS) fine[i] = 0;
-    if (tid == 0) {
-      s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
-      *s_thr = 0u;
-      *s_tl = CNB_NEG_INF;
-    }
+  };
+  auto clear_scalars = [&]() {  // tid 0
+    s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
+    *s_thr = 0u;
+    *s_tl = CNB_NEG_INF;
   };
   // one warp: refresh the histogram threshold (and its logit-space image)
   auto refresh_thr = [&]() {
@@ -853,32 +973,41 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       s_arr[s] = 0;
     }
     mbar_fence_init();
-  }
-  reset_state();
-  __syncthreads();
-  if (tid == 0) {
+    clear_scalars();
     for (int u = 0; u < SEL_STAGES && u < total_units; ++u) issue(u);
   }
+  clear_hist();
+  // First / last CTA of the first / last image this CTA touches (every image in between starts and ends
+  // inside this CTA's range): two binary searches over the plan, hidden behind the first TMA load.
+  const int img_lo = (int)(p_begin / C), img_hi = (int)((p_end - 1) / C);
+  if (tid == 32) s_tmp[26] = plan_cta_of_plane(pl, (long long)img_lo * C);
+  if (tid == 64) s_tmp[27] = plan_cta_of_plane(pl, (long long)(img_hi + 1) * C - 1);
+  __syncthreads();
+  const int i0_first = s_tmp[26], i1_last = s_tmp[27];
 
-  // push one qualifying pixel (any lane of any warp, concurrently)
-  auto push = [&](float v, uint32_t flat) {
+  // one qualifying pixel (any lane of any warp, concurrently)
+  auto push = [&](float v, uint32_t flat, int mode) {
     if (pl.clamp_one) v = fminf(v, 1.0f);
     const uint32_t bits = __float_as_uint(v);
-    const int hb = hist_bin(bits);
-    atomicAdd(&fine[hb], 1);
-    atomicAdd(&coarse[hb >> 6], 1);
-    const int slot = atomicAdd(&s_cnt[0], 1);
-    if (slot < SEL_CAP) buf[slot] = make_key(bits, flat);
-    else s_cnt[1] = 1;
+    if (mode != SW_KEYS) {
+      const int hb = hist_bin(bits);
+      atomicAdd(&fine[hb], 1);
+      if (mode == SW_BOTH) atomicAdd(&coarse[hb >> 6], 1);
+    }
+    if (mode != SW_HIST) {
+      const int slot = atomicAdd(&s_cnt[0], 1);
+      if (slot < SEL_CAP) buf[slot] = make_key(bits, flat);
+      else s_cnt[1] = 1;
+    }
   };
 
   // LOGITS: pixel with logit b whose 3x3 logit maximum is M
-  auto try_push_logit = [&](float b, float M, uint32_t flat) {
+  auto try_push_logit = [&](float b, float M, uint32_t flat, int mode) {
     bool pk = (b == M);
     if (!pk && (M - b) <= collide_margin(M)) pk = (sigmoid_ref(b) == sigmoid_ref(M));
     if (pk) {
       const float sv = sigmoid_ref(b);
-      if (sv > 0.0f) push(sv, flat);
+      if (sv > 0.0f) push(sv, flat, mode);
     }
   };
 
@@ -911,17 +1040,10 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   };
 
   // ---- CTA-wide flush of image `img` (all threads; called at image boundaries only)
-  long long t_sync = 0, t_fin = 0, t_cut = 0;
-  int n_rescan = 0, n_fin = 0, n_prune = 0;
   auto flush = [&](int img) {
-    long long tf0 = clock64();
     __syncthreads();
-    t_sync += clock64() - tf0;
-    tf0 = clock64();
-    const u64 *outp = buf;
     int n_out;
     if (s_cnt[1]) {
-      ++n_rescan;
       // the buffer overflowed at some point: rebuild this CTA's segment exactly from global memory
       __syncthreads();
       if (tid == 0) s_cnt[0] = 0;
@@ -958,19 +1080,21 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       if (cnt > pl.seg_cap) {                       // still too many (ties in the threshold bin): exact cut
         cta_prune(buf, s_cnt, K);
         n_out = min(cnt, K);
-        ++n_prune;
       }
     }
-    t_cut += clock64() - tf0;
-    if (tid == 0) {
-      s_tmp[28] = plan_cta_of_plane(pl, (long long)img * C);
-      s_tmp[29] = plan_cta_of_plane(pl, (long long)(img + 1) * C - 1);
+    const int i0 = (img == img_lo) ? i0_first : me;
+    const int i1 = (img == img_hi) ? i1_last : me;
+    if (i0 == i1) {
+      // the image lies entirely in this CTA: no segment, no ticket -- finalize from shared memory
+      finalize_hot(src, pl, img, 1, true, n_out, cand, cand_cnt, cand_thr, fout, buf, s_fcnt, s_tmp, s_red);
+      clear_hist();
+      if (tid == 0) clear_scalars();
+      __syncthreads();
+      return;
     }
-    __syncthreads();
-    const int i0 = s_tmp[28];
-    const int slot = (int)blockIdx.x - i0;
+    const int slot = me - i0;
     u64 *dst = cand + ((size_t)img * pl.max_slots + slot) * pl.seg_cap;
-    for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = outp[t];
+    for (int t = tid; t < n_out; t += SEL_THREADS) dst[t] = buf[t];
     if (tid == 0) {
       cand_cnt[(size_t)img * pl.max_slots + slot] = n_out;
       // histogram threshold = valid lower bound of the image's K-th best (0 after an exact rebuild)
@@ -978,26 +1102,25 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_cnt[2] = (atomicAdd(&img_done[img], 1) == s_tmp[29] - i0) ? 1 : 0;
+    int ticket = 0;
+    if (tid == 0) ticket = atomicAdd(&img_done[img], 1);   // in flight while the histogram is cleared
+    clear_hist();
+    if (tid == 0) s_cnt[2] = (ticket == i1 - i0) ? 1 : 0;
     __syncthreads();
     if (s_cnt[2]) {  // every segment of this image is in global memory: merge + emit here
-      const long long tq = clock64();
       __threadfence();
-      finalize_image<true, CtaGroup>(src, pl, img, cand, cand_cnt, fout, buf, s_tmp, s_red, cand_thr);
-      t_fin += clock64() - tq;
-      ++n_fin;
+      finalize_hot(src, pl, img, i1 - i0 + 1, false, 0, cand, cand_cnt, cand_thr, fout, buf, s_fcnt, s_tmp, s_red);
     }
-    __syncthreads();
-    reset_state();
+    if (tid == 0) clear_scalars();
     __syncthreads();
   };
 
   // ---- phase A + push of rows [y0, y0 + 4) of the plane in stage `st`
   // Per row: 4 vertical FMNMX3, 2 SHFL, 2 FADD (lane-edge -inf, keeps the ALU pipe free), the
   // horizontal max with the running threshold folded in, 4 compares and one (rarely taken) branch.
-  const bool first = (lane == 0);
   const float edge_l = (lane == 0) ? NI : 0.0f, edge_r = (lane == 31) ? NI : 0.0f;
-  auto sweep = [&](const float *st, int c, bool use_thr, int i_lo, int i_hi) {
+  auto sweep = [&](const float *st, int c, int mode) {
+    const bool use_thr = (mode != SW_HIST);
     const int y0 = warp * 4;
     const float *p = st + (size_t)y0 * 128 + lane * 4;
     const float4 ninf = make_float4(NI, NI, NI, NI);
@@ -1009,7 +1132,6 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     const uint32_t fbase = (uint32_t)c * (uint32_t)HW + (uint32_t)(y0 * 128 + lane * 4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (i < i_lo || i >= i_hi) continue;   // warp-uniform (bootstrap sweeps a row subset)
       // threshold >= smallest positive float, so `b == max(.., thr)` also rejects b <= 0; it is
       // re-read per row (one broadcast LDS): fresher threshold = fewer pushes
       const float4 a = r_[i], b = r_[i + 1], cc = r_[i + 2];
@@ -1024,10 +1146,10 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
         const bool q0 = b.x >= tl, q1 = b.y >= tl, q2 = b.z >= tl, q3 = b.w >= tl;
         if (q0 | q1 | q2 | q3) {
           const uint32_t f = fbase + (uint32_t)(i * 128);
-          if (q0) try_push_logit(b.x, fmax3(l, v0, v1), f);
-          if (q1) try_push_logit(b.y, fmax3(v0, v1, v2), f + 1);
-          if (q2) try_push_logit(b.z, fmax3(v1, v2, v3), f + 2);
-          if (q3) try_push_logit(b.w, fmax3(v2, v3, r), f + 3);
+          if (q0) try_push_logit(b.x, fmax3(l, v0, v1), f, mode);
+          if (q1) try_push_logit(b.y, fmax3(v0, v1, v2), f + 1, mode);
+          if (q2) try_push_logit(b.z, fmax3(v1, v2, v3), f + 2, mode);
+          if (q3) try_push_logit(b.w, fmax3(v2, v3, r), f + 3, mode);
         }
         continue;
       }
@@ -1039,47 +1161,42 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       const bool q3 = (b.w == fmax3(m23, r, thr_f));
       if (q0 | q1 | q2 | q3) {  // rare: a few pixels per plane once the threshold exists
         const uint32_t f = fbase + (uint32_t)(i * 128);
-        if (q0) push(b.x, f);
-        if (q1) push(b.y, f + 1);
-        if (q2) push(b.z, f + 2);
-        if (q3) push(b.w, f + 3);
+        if (q0) push(b.x, f, mode);
+        if (q1) push(b.y, f + 1, mode);
+        if (q2) push(b.z, f + 2, mode);
+        if (q3) push(b.w, f + 3, mode);
       }
     }
   };
 
-  int img = (int)(p_begin / C), c = (int)(p_begin - (long long)img * C);
+  int img = img_lo, c = (int)(p_begin - (long long)img * C);
   int stage = 0, par = 0;
   bool fresh = true;  // first unit of an image in this CTA (CTA-uniform)
-  const long long t_start = clock64();
-  long long t_wait = 0, t_boot = 0, t_flush = 0;
-  int n_flush = 0;
   for (int u = 0; u < total_units; ++u) {
     const float *st = stages + (size_t)stage * (SEL_STAGE_BYTES / 4);
-    long long t0 = clock64();
     mbar_wait(&full[stage], (uint32_t)par);
-    t_wait += clock64() - t0;
-    t0 = clock64();
     if (*(volatile int *)&s_flag[u & 3]) compact(u & 3);   // set 3 units ago, before this plane's TMA was issued
     if (fresh) {
-      // bootstrap: every warp first sweeps only its first row (a 25% sample of the plane, all warps
-      // busy), a threshold is derived, then the remaining rows are swept against it and the
-      // threshold is refreshed once more, so unit 1 already sees the K-th best of a whole plane.
-      sweep(st, c, false, 0, 1);
+      // bootstrap (see header): histogram-only pass, K-th best of the plane, key pass
+      sweep(st, c, SW_HIST);
+      __syncthreads();
+      {  // one coarse bin per warp: sum of its 64 fine bins
+        int sum = fine[warp * 64 + lane] + fine[warp * 64 + 32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) coarse[warp] = sum;
+      }
       __syncthreads();
       if (warp == 0) refresh_thr();
       __syncthreads();
-      sweep(st, c, true, 1, 4);
-      __syncthreads();
-      if (warp == 0) refresh_thr();
-      __syncthreads();
+      sweep(st, c, SW_KEYS);
       fresh = false;
-      t_boot += clock64() - t0;
     } else {
-      sweep(st, c, true, 0, 4);
+      sweep(st, c, SW_BOTH);
+      if (warp == (u & (SEL_WARPS - 1))) refresh_thr();  // partial counts are valid too
     }
-    if (warp == (u & (SEL_WARPS - 1))) refresh_thr();  // partial counts are valid too
     __syncwarp();
-    if (first) {
+    if (lane == 0) {
       // last warp to finish this stage re-arms it (no waiting): TMA load of unit u+3
       __threadfence_block();
       if (atomicAdd(&s_arr[stage], 1) == SEL_WARPS - 1) {
@@ -1093,36 +1210,15 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       }
     }
     // next unit
-    t0 = clock64();
     if (++c == C) {
       flush(img);
       c = 0;
       ++img;
       fresh = true;
-      t_flush += clock64() - t0;
-      ++n_flush;
     } else if (u == total_units - 1) {
       flush(img);
-      t_flush += clock64() - t0;
-      ++n_flush;
     }
     if (++stage == SEL_STAGES) { stage = 0; par ^= 1; }
-  }
-  if (pl.dbg && tid == 0) {
-    unsigned long long *d = pl.dbg + (size_t)blockIdx.x * 8;
-    d[0] = (unsigned long long)(clock64() - t_start);
-    d[1] = (unsigned long long)t_wait;
-    d[2] = (unsigned long long)t_boot;
-    d[3] = (unsigned long long)t_flush;
-    d[4] = (unsigned long long)n_flush;
-    d[5] = (unsigned long long)total_units;
-    unsigned int smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    d[6] = smid;
-    d[7] = (unsigned long long)n_fin | ((unsigned long long)n_rescan << 8) | ((unsigned long long)n_prune << 16);
-    d[6] = (unsigned long long)t_sync;
-    d[5] = (unsigned long long)t_cut;
-    d[4] = (unsigned long long)n_flush | ((unsigned long long)t_fin << 8);
   }
 }
 
@@ -1144,8 +1240,6 @@ static size_t stage1_smem_bytes() {
          (size_t)(SEL_HIST_FINE + SEL_HIST_COARSE) * 4 + (size_t)SEL_MASK_WORDS * 4 + SEL_STAGES * 8 + 32;
 }
 
-static thread_local unsigned long long *t_dbg = nullptr;
-extern "C" void cnb_debug_set_select_stats(void *p) { t_dbg = reinterpret_cast<unsigned long long *>(p); }
 
 int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, int nms, SelectPlan *pl) {
   CNB_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0 && K > 0, CNB_EINVAL,
@@ -1157,7 +1251,6 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   pl->n_img = n_img; pl->C = C; pl->H = H; pl->W = W; pl->K = K; pl->nms = nms;
   pl->clamp_one = 0;
   pl->logits = 0;
-  pl->dbg = t_dbg;
   pl->Wp = (W + 3) / 4 * 4;
   pl->ncb = (W + 127) / 128;
   pl->P = (long long)n_img * C;
@@ -1174,10 +1267,12 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   int n_cta = num_sms();
   if (n_cta > SEL_MAX_CTA) n_cta = SEL_MAX_CTA;
   if ((long long)n_cta > pl->P) n_cta = (int)pl->P;
-  // image boundaries cost the crossing CTA ~7 planes' worth of cycles in the hot kernel
-  // (measured: flush + bootstrap + finalize); only worth modelling when ranges are long
+  // hot geometry: whole 128x128 planes through the warp-asynchronous kernel with its own fused finalize
+  // (any number of segments per image, so no grid shrinking).  An image boundary costs the crossing CTA a
+  // flush + a bootstrap, about 2 planes' worth of cycles; only worth modelling when ranges are long.
+  const bool hot_geom = nms && pl->use_tma && W == 128 && H == 128 && pl->rb == 128 && K <= 256;
   int wb = 0;
-  if (nms && pl->use_tma && W == 128 && H == 128 && K <= 256 && C > 1 && pl->P / n_cta >= 16) wb = 7;
+  if (hot_geom && C > 1 && pl->P / n_cta >= 8) wb = 2;
   for (;;) {
     Part q;
     q.P = pl->P; q.n_cta = n_cta; q.C = C; q.wb = wb;
@@ -1193,7 +1288,7 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
       const int i1 = cta_of_plane((long long)(b + 1) * C - 1, q);
       if (i1 - i0 + 1 > ms) ms = i1 - i0 + 1;
     }
-    if ((long long)ms * K <= SEL_FIN_MAX || n_cta == 1) {
+    if (hot_geom || (long long)ms * K <= SEL_FIN_MAX || n_cta == 1) {
       pl->max_slots = ms;
       break;
     }
@@ -1209,9 +1304,10 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   pl->fused_finalize = ((long long)pl->max_slots * K <= SEL_CAP) ? 1 : 0;
   pl->seg_cap = K;
   pl->hot = 0;
-  if (nms && pl->use_tma && W == 128 && H == 128 && pl->rb == 128 && pl->fused_finalize && K <= 256) {
+  if (hot_geom) {
     pl->hot = 1;
-    if (K <= 128 && (long long)pl->max_slots * 256 <= SEL_CAP) pl->seg_cap = 256;
+    pl->fused_finalize = 1;
+    if (K <= 128) pl->seg_cap = 256;
   }
   return CNB_OK;
 }

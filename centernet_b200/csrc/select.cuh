@@ -35,7 +35,6 @@ struct SelectPlan {
   int hot;        // 128x128 planes, TMA, NMS, fused finalize, K <= 256: warp-asynchronous kernel
   int wb;         // partition weight of an image boundary, in planes (flush + bootstrap + finalize cost)
   long long P;    // planes = n_img * C
-  unsigned long long *dbg;  // optional per-CTA cycle counters (tuning only; null in normal use)
   int cta_start[SEL_MAX_CTA + 1];  // first plane of every CTA's contiguous range (host-computed partition)
 };
 

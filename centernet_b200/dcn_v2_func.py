@@ -7,6 +7,7 @@ cnb_dcnv2_backward (im2col-free, no `ones`/`columns` scratch).  Non-CUDA tensors
 NotImplementedError exactly like the reference (:23-24, :41-42).
 """
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -23,13 +24,40 @@ def _out_hw(h, w, kh, kw, stride, padding, dilation):
     return ho, wo
 
 
+_WT_CACHE = {}      # id(weight) -> (weakref to it, its version when tiled, tiles); evicted when the tensor dies
+
+
+def _weight_tiles(weight, dg):
+    """TF32 hi/lo weight tiles in the UMMA layout (cnb_dcnv2_prepare_weights), rebuilt only when the parameter
+    changes: torch bumps `_version` on every in-place update (optimizer step, load_state_dict), and the entry
+    is tied to the tensor OBJECT by a weak reference, so a new tensor that happens to reuse the address never
+    sees stale tiles."""
+    w = f32c(weight)
+    cout, cin, kh, kw = [int(v) for v in w.shape]
+    own = w is weight or w.data_ptr() == weight.data_ptr()
+    key = id(weight)
+    ver = weight._version
+    hit = _WT_CACHE.get(key) if own else None
+    if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == w.device:
+        return hit[2]
+    nbytes = C.dcnv2_wtiles_bytes(cin, cout, kh, kw, dg)
+    wt = workspace(nbytes, w.device)
+    C.dcnv2_prepare_weights(ptr(w), cin, cout, kh, kw, dg, ptr(wt), wt.numel(), stream_ptr(w))
+    if own:
+        try:
+            _WT_CACHE[key] = (weakref.ref(weight, lambda _r, k=key: _WT_CACHE.pop(k, None)), ver, wt)
+        except TypeError:      # not weak-referenceable: do not cache
+            pass
+    return wt
+
+
 class _DCNv2(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias, stride, padding, dilation, deformable_groups):
         if not input.is_cuda:
             raise NotImplementedError
-        x, off, msk, w, b = f32c(input), f32c(offset), f32c(mask), f32c(weight), f32c(bias)
-        n, cin, h, wd = [int(v) for v in x.shape]
+        off, msk, w, b = f32c(offset), f32c(mask), f32c(weight), f32c(bias)
+        n, cin, h, wd = [int(v) for v in input.shape]
         cout, cin_w, kh, kw = [int(v) for v in w.shape]
         if cin_w != cin:   # dcn_v2_cuda.c:36-38
             raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (cin, cin_w))
@@ -38,14 +66,28 @@ class _DCNv2(Function):
         if tuple(off.shape) != (n, 2 * kt * deformable_groups, ho, wo) or \
                 tuple(msk.shape) != (n, kt * deformable_groups, ho, wo):
             raise RuntimeError("DCNv2: offset/mask shape does not match the output grid")
-        out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
-        ws_bytes = 0 if _FORCE_FP32 else C.dcnv2_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding,
-                                                                 dilation, deformable_groups)
-        ws = workspace(ws_bytes, x.device) if ws_bytes else None
-        C.dcnv2_forward(ptr(x), ptr(off), ptr(msk), ptr(w), ptr(b), ptr(out), n, cin, h, wd, cout, kh, kw,
-                        stride, stride, padding, padding, dilation, dilation, deformable_groups, ptr(ws),
-                        ws.numel() if ws is not None else 0, stream_ptr(x))
-        ctx.save_for_backward(x, off, msk, w, b)
+        out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=input.device)
+        # a channels_last activation (what cuDNN produces under torch.channels_last) is sampled in place
+        nhwc = (not _FORCE_FP32) and kt <= 9 and (cin // deformable_groups) % 32 == 0 and \
+            input.dtype == torch.float32 and input.is_contiguous(memory_format=torch.channels_last) and \
+            not input.is_contiguous()
+        need_grad = any(ctx.needs_input_grad[:5])
+        x = f32c(input) if (need_grad or not nhwc) else None      # NCHW copy only when somebody needs it
+        if _FORCE_FP32 or kt > 9:
+            C.dcnv2_forward(ptr(x), ptr(off), ptr(msk), ptr(w), ptr(b), ptr(out), n, cin, h, wd, cout, kh, kw,
+                            stride, stride, padding, padding, dilation, dilation, deformable_groups, 0, 0,
+                            stream_ptr(x))
+        else:
+            # tensor-core path: weight tiles cached per weight version; NCHW inputs go through one re-layout pass
+            wt = _weight_tiles(weight, deformable_groups)
+            xin = input if nhwc else x
+            ws = workspace(C.dcnv2_prepared_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding, dilation,
+                                                            deformable_groups), input.device)
+            C.dcnv2_forward_prepared(ptr(xin), int(nhwc), ptr(off), ptr(msk), ptr(wt), ptr(b), ptr(out), n, cin, h, wd,
+                                     cout, kh, kw, stride, stride, padding, padding, dilation, dilation,
+                                     deformable_groups, ptr(ws), ws.numel(), stream_ptr(off))
+        if need_grad:
+            ctx.save_for_backward(x, off, msk, w, b)
         ctx.cfg = (stride, padding, dilation, deformable_groups)
         return out
 

@@ -194,9 +194,11 @@ int cnb_reg_loss(const float *output, const void *mask, const int64_t *ind, cons
  * grad_input/grad_offset/grad_mask, all of which must arrive zero-filled as in
  * dcn_v2_func.py:44-48.
  * Forward workspace (cnb_dcnv2_workspace_bytes, 16-byte aligned): the weights
- * re-tiled for the tensor-core path plus a channels-last copy of the input;
- * the query returns 0 for kernels with more than 9 taps.  workspace == NULL
- * (or smaller than the query) selects the fp32 CUDA-core forward instead. */
+ * re-tiled for the tensor-core path, a channels-last copy of the input and, for
+ * maps too small to fill the GPU, split-K partial sums; the query returns 0 for
+ * kernels with more than 9 taps.  workspace == NULL (or smaller than the query,
+ * or anisotropic stride/pad/dilation) selects the fp32 CUDA-core forward instead.
+ * cnb_dcnv2_backward ignores its workspace arguments (kept for ABI stability). */
 size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
                                  int stride, int pad, int dil, int dg);
 int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask,
@@ -205,6 +207,23 @@ int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask
                       int stride_h, int stride_w, int pad_h, int pad_w,
                       int dil_h, int dil_w, int deformable_groups,
                       void *workspace, size_t workspace_bytes, void *stream);
+/* Steady-state form of the forward (what the Python module uses): the weight
+ * tiles (TF32 hi/lo split, UMMA layout) are built ONCE per weight version into a
+ * caller-owned buffer of cnb_dcnv2_wtiles_bytes and reused by every call;
+ * input_channels_last != 0 says `input` already is [b][h*w][cin] (torch
+ * channels_last) so no re-layout pass runs (needs cin/dg % 32 == 0, else the flag
+ * is ignored and `input` must be NCHW).  workspace: cnb_dcnv2_prepared_workspace_bytes. */
+size_t cnb_dcnv2_wtiles_bytes(int cin, int cout, int kh, int kw, int dg);
+int cnb_dcnv2_prepare_weights(const float *weight, int cin, int cout, int kh, int kw,
+                              int deformable_groups, void *wtiles, size_t wtiles_bytes, void *stream);
+size_t cnb_dcnv2_prepared_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
+                                          int stride, int pad, int dil, int dg);
+int cnb_dcnv2_forward_prepared(const float *input, int input_channels_last, const float *offset,
+                               const float *mask, const void *wtiles, const float *bias, float *output,
+                               int b, int cin, int h, int w, int cout, int kh, int kw,
+                               int stride_h, int stride_w, int pad_h, int pad_w,
+                               int dil_h, int dil_w, int deformable_groups,
+                               void *workspace, size_t workspace_bytes, void *stream);
 int cnb_dcnv2_backward(const float *input, const float *offset, const float *mask,
                        const float *weight, const float *grad_output,
                        float *grad_input, float *grad_offset, float *grad_mask,
