@@ -151,6 +151,27 @@ PYBIND11_MODULE(_C, m) {
                        ptr<void>(stream)),
           "cnb_reg_loss");
   });
+  m.def("post_transform", [](P rows, P out, P trans, int b, int n, int d, int a0, int na, int b0, int nb, P stream) {
+    check(cnb_post_transform(ptr<const float>(rows), ptr<float>(out), ptr<const double>(trans), b, n, d, a0, na, b0, nb,
+                             ptr<void>(stream)),
+          "cnb_post_transform");
+  });
+  m.def("group_by_class", [](P dets, int b, int n, int nc, P rows, P offsets, P stream) {
+    check(cnb_group_by_class(ptr<const float>(dets), b, n, nc, ptr<float>(rows), ptr<int32_t>(offsets),
+                             ptr<void>(stream)),
+          "cnb_group_by_class");
+  });
+  m.def("soft_nms", [](P rows, P out, P offsets, int n_img, int lists, int n_cap, int d, float sigma, float nt,
+                       float thr, int method, P final_n, P stream) {
+    check(cnb_soft_nms(ptr<const float>(rows), ptr<float>(out), ptr<const int32_t>(offsets), n_img, lists, n_cap, d,
+                       sigma, nt, thr, method, ptr<int32_t>(final_n), ptr<void>(stream)),
+          "cnb_soft_nms");
+  });
+  m.def("topk_keep", [](P rows, int b, int n_cap, int d, P offsets, int nc, int mpi, P keep, P thresh, P stream) {
+    check(cnb_topk_keep(ptr<const float>(rows), b, n_cap, d, ptr<const int32_t>(offsets), nc, mpi, ptr<uint8_t>(keep),
+                        ptr<float>(thresh), ptr<void>(stream)),
+          "cnb_topk_keep");
+  });
   m.def("dcnv2_workspace_bytes", &cnb_dcnv2_workspace_bytes);
   m.def("dcnv2_forward", [](P input, P offset, P mask, P weight, P bias, P output, int b, int cin, int h, int w,
                             int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg, P ws,

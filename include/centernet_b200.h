@@ -254,6 +254,37 @@ int cnb_psroi_pooling_backward(const float *grad_out, const float *data, const f
                                int pooled_size, int part_size, int sample_per_part, float trans_std,
                                void *stream);
 
+/* ------------------------------------------- N2: detection post-processing
+ * Device-side replacements of utils/post_process.py:83-114 (ctdet_post_process,
+ * multi_pose_post_process), external/nms.pyx:77-275 (soft_nms, soft_nms_39) and
+ * detectors/ctdet.py:76-92 (merge_outputs): the detections stay on the GPU
+ * from decode to the final per-class lists.
+ *
+ * cnb_post_transform: rows [b,n,d] -> out [b,n,d]; the (x,y) pairs at columns
+ *   [a0, a0+2*na) and [b0, b0+2*nb) are mapped through the image's 2x3 float64
+ *   matrix trans[b][6] (the inverse affine of utils/image.py:27-60, computed by
+ *   the caller on the host), every other column is copied.
+ * cnb_group_by_class: dets [b,n,6] (x1,y1,x2,y2,score,class) -> rows [b,n,5]
+ *   grouped by class, input order kept inside a class; offsets [b,classes+1].
+ * cnb_soft_nms: one list per (image, class): rows image*n_cap +
+ *   [offsets[image][c], offsets[image][c+1]) of `rows` ([*,d], d = 5 or 39;
+ *   extra columns follow soft_nms_39's swap rule).  The array, rows beyond the
+ *   final length included, ends exactly as the reference's in-place routine
+ *   leaves it; final_n (nullable, [n_img*lists_per_img]) receives len(keep)
+ *   (negative: list longer than 1536 rows, left untouched).  out may alias rows
+ *   only when d == 5.  method 0 hard, 1 linear, 2 gaussian.
+ * cnb_topk_keep: keep[b,n_cap] = score >= (max_per_image-th largest score of
+ *   the image's offsets[b][classes] rows); thresh (nullable) [b]. */
+int cnb_post_transform(const float *rows, float *out, const double *trans, int b, int n, int d,
+                       int a0, int na, int b0, int nb, void *stream);
+int cnb_group_by_class(const float *dets, int b, int n, int num_classes, float *rows,
+                       int32_t *offsets, void *stream);
+int cnb_soft_nms(const float *rows, float *out, const int32_t *offsets, int n_img, int lists_per_img,
+                 int n_cap, int d, float sigma, float nt, float threshold, int method,
+                 int32_t *final_n, void *stream);
+int cnb_topk_keep(const float *rows, int b, int n_cap, int d, const int32_t *offsets, int num_classes,
+                  int max_per_image, uint8_t *keep, float *thresh, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

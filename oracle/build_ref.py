@@ -47,5 +47,58 @@ def build(force=False):
     return LIB
 
 
+# ---------------------------------------------------------------- the reference's Cython soft-NMS (N2 oracle pin)
+REF_NMS = "/root/reference/src/lib/external/nms.pyx"
+
+
+def nms_lib_path():
+    import sysconfig
+    return os.path.join(OUT, "nms" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_nms(force=False):
+    """oracle/_ref/nms<ext>.so = the reference's src/lib/external/nms.pyx (soft_nms :77-169, soft_nms_39 :171-275)
+    through cython + gcc.  The file is compiled as it lies except for ONE declaration outside those functions:
+    `np.int_t` (the hard-NMS helper `nms`, :32) no longer exists in NumPy 2 and is retyped `np.intp_t` in a
+    temporary copy that is deleted after the build (nothing of the reference enters the repository)."""
+    import shutil
+    import sysconfig
+    import tempfile
+    lib = nms_lib_path()
+    if not os.path.exists(REF_NMS):
+        return lib if os.path.exists(lib) else None
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(REF_NMS):
+        return lib
+    import numpy
+    os.makedirs(OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="cnb_nms_")
+    try:
+        src = open(REF_NMS).read().replace("np.int_t", "np.intp_t")
+        with open(os.path.join(tmp, "nms.pyx"), "w") as f:
+            f.write(src)
+        for cmd in (["cython", "-3", os.path.join(tmp, "nms.pyx"), "-o", os.path.join(tmp, "nms.c")],
+                    ["gcc", "-O2", "-shared", "-fPIC", "-Wno-cpp", "-Wno-unused-function", "-I" + numpy.get_include(),
+                     "-I" + sysconfig.get_paths()["include"], os.path.join(tmp, "nms.c"), "-o", lib]):
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("oracle/_ref nms build failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return lib
+
+
+def load_nms():
+    """The compiled reference module (or None when it was never built)."""
+    import importlib.util
+    path = build_nms()
+    if path is None or not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("nms", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_nms(force="--force" in sys.argv))
