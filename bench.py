@@ -333,6 +333,12 @@ def main():
     secondary = {"ctdet_decode_from_logits": {"value": logit_value, "unit": UNIT,
                                               "note": "same workload, input = pre-sigmoid logits, sigmoid fused "
                                                       "into the selection kernel (one launch, no heat map written)"}}
+    if world > 1 and not args.no_secondary:       # collective: every rank takes part (E2, training-side exchange)
+        try:
+            import bench_secondary
+            secondary.update(bench_secondary.run_allreduce(dev, world, rank))
+        except Exception as e:
+            secondary["grad_allreduce_dla34"] = {"failed": str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_secondary:
         try:
             import bench_secondary
