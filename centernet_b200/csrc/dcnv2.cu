@@ -494,7 +494,8 @@ int dcn_prepare_weights_tc(const float *weight, int cin, int cout, int kh, int k
 int dcn_forward_tc_prepared(const float *input, int input_nhwc, const float *offset, const float *mask,
                             const float *wtiles, const float *bias, float *output, int b, int cin, int h, int w,
                             int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
-                            void *workspace, cudaStream_t stream);
+                            void *workspace, cudaStream_t stream, int fused_offset_mask, const float *epi_scale,
+                            const float *epi_shift, int relu);
 int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
                    const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
                    int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream);
@@ -564,7 +565,31 @@ int cnb_dcnv2_forward_prepared(const float *input, int input_channels_last, cons
               CNB_EINVAL, "cnb_dcnv2_forward_prepared: buffers must be 16-byte aligned");
   return dcn_forward_tc_prepared(input, input_channels_last, offset, mask, reinterpret_cast<const float *>(wtiles),
                                  bias, output, b, cin, h, w, cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h,
-                                 dil_w, deformable_groups, workspace, (cudaStream_t)stream_);
+                                 dil_w, deformable_groups, workspace, (cudaStream_t)stream_, 0, nullptr, nullptr, 0);
+}
+
+int cnb_dcnv2_forward_fused(const float *input, int input_channels_last, const float *offset_mask, const void *wtiles,
+                            const float *bias, const float *bn_scale, const float *bn_shift, int relu, float *output,
+                            int b, int cin, int h, int w, int cout, int kh, int kw, int stride, int pad, int dil,
+                            int deformable_groups, void *workspace, size_t workspace_bytes, void *stream_) {
+  CNB_REQUIRE(input && offset_mask && wtiles && output && workspace, CNB_EINVAL,
+              "cnb_dcnv2_forward_fused: null pointer");
+  CNB_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), CNB_EINVAL,
+              "cnb_dcnv2_forward_fused: bn_scale and bn_shift go together");
+  DcnShape s;
+  int rc = check_shape("cnb_dcnv2_forward_fused", b, cin, h, w, cout, kh, kw, stride, stride, pad, pad, dil, dil,
+                       deformable_groups, &s);
+  if (rc != CNB_OK) return rc;
+  CNB_REQUIRE(workspace_bytes >= dcn_tc_fwd_workspace_bytes(b, cin, h, w, cout, kh, kw, stride, pad, dil,
+                                                            deformable_groups),
+              CNB_EWORKSPACE, "cnb_dcnv2_forward_fused: workspace too small");
+  CNB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 && (reinterpret_cast<uintptr_t>(wtiles) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(input) & 15u) == 0,
+              CNB_EINVAL, "cnb_dcnv2_forward_fused: buffers must be 16-byte aligned");
+  return dcn_forward_tc_prepared(input, input_channels_last, offset_mask, nullptr,
+                                 reinterpret_cast<const float *>(wtiles), bias, output, b, cin, h, w, cout, kh, kw, stride,
+                                 stride, pad, pad, dil, dil, deformable_groups, workspace, (cudaStream_t)stream_, 1,
+                                 bn_scale, bn_shift, relu);
 }
 
 int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask, const float *weight,

@@ -60,6 +60,11 @@ struct DcnShapeTc {
   int tiles_x, tiles_y;
   int splits;     // K splits (channel-block ranges) per item; > 1 -> partial sums + k_dcn_reduce
   int n_items;    // B * tiles * n_cot * splits
+  // fused prologue / epilogue (N3, dcn_v2.py:64-70 + pose_dla_dcn.py:345-357)
+  long long off_bs, mask_bs;   // batch strides (floats) of the offset / mask tensors
+  int mask_logit;              // mask holds the raw conv_offset_mask output: sigmoid applied on the fly
+  int relu;                    // epilogue: y = relu(scale[o] * (acc + bias[o]) + shift[o])
+  const float *epi_scale, *epi_shift;   // folded inference BatchNorm (nullable)
 };
 
 struct __align__(16) TapMetaTc {
@@ -146,12 +151,16 @@ __global__ void __launch_bounds__(256) k_dcn_nhwc(const float *__restrict__ x, f
 // y[b][o][p] = bias[o] + sum_s part[s][b][o][p], s ascending (deterministic split-K epilogue)
 __global__ void __launch_bounds__(256) k_dcn_reduce(const float *__restrict__ part, const float *__restrict__ bias,
                                                     float *__restrict__ y, int splits, int cout, long long hwo,
-                                                    long long total) {
+                                                    long long total, const float *__restrict__ epi_scale,
+                                                    const float *__restrict__ epi_shift, int relu) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int o = (int)((i / hwo) % cout);
-    float v = bias ? __ldg(bias + o) : 0.f;
+    float v = 0.f;
     for (int s = 0; s < splits; ++s) v += __ldg(part + (long long)s * total + i);
+    if (bias) v += __ldg(bias + o);
+    if (epi_scale) v = fmaf(v, __ldg(epi_scale + o), __ldg(epi_shift + o));
+    if (relu) v = fmaxf(v, 0.f);
     y[i] = v;
   }
 }
@@ -239,9 +248,10 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
             if (ho < s.Ho && wo < s.Wo && t < KT) {
               const long long p = (long long)ho * s.Wo + wo;
               const int i = t / s.kw, j = t - i * s.kw;
-              const float *op = offset + ((long long)it.b * s.dg + g) * 2 * KT * HWo;
+              const float *op = offset + (long long)it.b * s.off_bs + (long long)g * 2 * KT * HWo;
               const float dy = __ldg(op + (2 * t) * HWo + p), dx = __ldg(op + (2 * t + 1) * HWo + p);
-              const float m = __ldg(mask + (((long long)it.b * s.dg + g) * KT + t) * HWo + p);
+              float m = __ldg(mask + (long long)it.b * s.mask_bs + ((long long)g * KT + t) * HWo + p);
+              if (s.mask_logit) m = 1.0f / (1.0f + expf(-m));        // torch.sigmoid(mask), dcn_v2.py:68
               const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + dy;
               const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + dx;
               if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {   // dcn_v2_im2col_cuda.cu:165
@@ -403,8 +413,13 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
           for (int j = 0; j < 32; ++j) {
             const int o = it.cot * CO_T + c32 + j;
             if (o < s.Cout) {
-              const float bv = (bias && s.splits == 1) ? __ldg(bias + o) : 0.f;
-              dst[(long long)o * HWo] = __uint_as_float(v[j]) + bv;
+              float r = __uint_as_float(v[j]);
+              if (s.splits == 1) {
+                if (bias) r += __ldg(bias + o);
+                if (s.epi_scale) r = fmaf(r, __ldg(s.epi_scale + o), __ldg(s.epi_shift + o));
+                if (s.relu) r = fmaxf(r, 0.f);
+              }
+              dst[(long long)o * HWo] = r;
             }
           }
         }
@@ -446,6 +461,11 @@ static void fill_shape(DcnShapeTc *s, int b, int cin, int h, int w, int cout, in
   }
   s->splits = splits;
   s->n_items = (int)(base_items * splits);
+  s->off_bs = (long long)dg * 2 * kh * kw * s->Ho * s->Wo;
+  s->mask_bs = (long long)dg * kh * kw * s->Ho * s->Wo;
+  s->mask_logit = 0;
+  s->relu = 0;
+  s->epi_scale = s->epi_shift = nullptr;
 }
 
 size_t dcn_tc_wtiles_bytes(int cin, int cout, int dg) {
@@ -502,9 +522,18 @@ static int launch_fwd(const float *xt, const float *offset, const float *mask, c
 int dcn_forward_tc_prepared(const float *input, int input_nhwc, const float *offset, const float *mask,
                             const float *wtiles, const float *bias, float *output, int b, int cin, int h, int w,
                             int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
-                            void *workspace, cudaStream_t stream) {
+                            void *workspace, cudaStream_t stream, int fused_offset_mask, const float *epi_scale,
+                            const float *epi_shift, int relu) {
   DcnShapeTc s;
   fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
+  if (fused_offset_mask) {   // `offset` is the raw [b, 3*kt*dg, ho, wo] output of conv_offset_mask; mask = its last third
+    s.off_bs = s.mask_bs = (long long)dg * 3 * kh * kw * s.Ho * s.Wo;
+    s.mask_logit = 1;
+    mask = offset + (long long)dg * 2 * kh * kw * s.Ho * s.Wo;
+  }
+  s.epi_scale = epi_scale;
+  s.epi_shift = epi_scale ? epi_shift : nullptr;
+  s.relu = relu;
   float *xt = reinterpret_cast<float *>(workspace);
   float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + tc_xt_bytes(s));
   const long long HW = (long long)h * w;
@@ -526,7 +555,8 @@ int dcn_forward_tc_prepared(const float *input, int input_nhwc, const float *off
   if (s.splits > 1) {
     const long long total = (long long)b * cout * s.Ho * s.Wo;
     const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    k_dcn_reduce<<<grid, 256, 0, stream>>>(part, bias, output, s.splits, cout, (long long)s.Ho * s.Wo, total);
+    k_dcn_reduce<<<grid, 256, 0, stream>>>(part, bias, output, s.splits, cout, (long long)s.Ho * s.Wo, total, s.epi_scale,
+                                           s.epi_shift, s.relu);
     CNB_CHECK_LAUNCH("cnb_dcnv2_forward split-K reduce");
     count_launch();
   }
@@ -542,7 +572,7 @@ int dcn_forward_tc(const float *input, const float *offset, const float *mask, c
   if (rc != CNB_OK) return rc;
   return dcn_forward_tc_prepared(input, 0, offset, mask, wt, bias, output, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw,
                                  dh, dw, dg, reinterpret_cast<char *>(workspace) + dcn_tc_wtiles_bytes(cin, cout, dg),
-                                 stream);
+                                 stream, 0, nullptr, nullptr, 0);
 }
 
 }  // namespace cnb

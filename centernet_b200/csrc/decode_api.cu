@@ -161,7 +161,48 @@ __global__ void __launch_bounds__(256) k_sigmoid(const float *__restrict__ x, fl
     if (i0 + j < n) out[i0 + j] = 1.0f / (1.0f + expf(-x[i0 + j]));
 }
 
+// Flip-test merge (detectors/ctdet.py:34-37, detectors/multi_pose.py:43-51): src [2n, c, h, w] holds the heads
+// of n images followed by those of their horizontally flipped copies; dst [n, c, h, w] =
+//   ( f(src[i, ch]) + sign[ch] * f(flip_w(src[n + i, perm[ch]])) ) / 2,     f = sigmoid (mode 1) or identity.
+// perm / sign (nullable) express flip_lr (joint swap, models/utils.py:33-39) and flip_lr_off (joint swap + negated
+// x offsets, :41-50); null = flip_tensor (:28-29).  One pass instead of the reference's sigmoid_, slices, host
+// round trip through numpy, add and divide.
+__global__ void __launch_bounds__(256) k_flip_merge(const float *__restrict__ src, float *__restrict__ dst, int n, int c,
+                                                    int h, int w, int mode, const int *__restrict__ perm,
+                                                    const float *__restrict__ sign) {
+  const long long total = (long long)n * c * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    long long r = i / w;
+    const int y = (int)(r % h);
+    r /= h;
+    const int ch = (int)(r % c), img = (int)(r / c);
+    const int pc = perm ? perm[ch] : ch;
+    float a = src[i];
+    float b = src[(((long long)(n + img) * c + pc) * h + y) * w + (w - 1 - x)];
+    if (mode == 1) {
+      a = 1.0f / (1.0f + expf(-a));
+      b = 1.0f / (1.0f + expf(-b));
+    }
+    if (sign) b = __fmul_rn(b, sign[ch]);
+    dst[i] = __fadd_rn(a, b) / 2.0f;
+  }
+}
+
 extern "C" {
+
+int cnb_flip_merge(const float *src, float *dst, int n, int c, int h, int w, int apply_sigmoid, const int32_t *perm,
+                   const float *sign, void *stream) {
+  CNB_REQUIRE(src && dst, CNB_EINVAL, "cnb_flip_merge: null pointer");
+  CNB_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, CNB_EINVAL, "cnb_flip_merge: non-positive dimension");
+  const long long total = (long long)n * c * h * w;
+  const int grid = (int)((total + 255) / 256 < 4736 ? (total + 255) / 256 : 4736);
+  k_flip_merge<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, n, c, h, w, apply_sigmoid ? 1 : 0, perm, sign);
+  CNB_CHECK_LAUNCH("cnb_flip_merge");
+  count_launch();
+  return CNB_OK;
+}
 
 int cnb_nms(const float *heat, float *out, int n, int c, int h, int w, void *stream) {
   CNB_REQUIRE(heat && out, CNB_EINVAL, "cnb_nms: null pointer");

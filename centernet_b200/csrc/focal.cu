@@ -33,11 +33,63 @@ __device__ __forceinline__ float gauss_value(int dx, int dy, int r) {
   return (float)exp(-(double)(dx * dx + dy * dy) / (2.0 * sigma * sigma));
 }
 
-__device__ __forceinline__ float target_at(const Obj *objs, int n, int x, int y) {
+// Gaussian tables (shared memory).  exp(-(dx^2+dy^2)/(2 sigma^2)) depends on d2 = dx^2 + dy^2 only, so every
+// object gets a table over d2 in [0, 2 r^2] -- about half the size of its (2r+1)^2 window -- filled once per
+// plane by all threads (one float64 exp per ENTRY, no divergence) instead of one exp per covered pixel inside
+// a divergent warp.  Same expression, same float64 -> fp32 rounding: bit-identical targets.  Objects whose
+// table does not fit keep the direct evaluation.
+constexpr int GAUSS_TAB_FLOATS = 6144;   // 24 KB
+struct ObjTab { int off; };              // table start, or -1 (direct evaluation)
+
+__device__ __forceinline__ void build_tables(const Obj *objs, int n, ObjTab *tabs, float *tab, int *s_total) {
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < n; ++i) {
+      const long long sz = 2ll * objs[i].r * objs[i].r + 1;
+      if (run + sz <= GAUSS_TAB_FLOATS) { tabs[i].off = run; run += (int)sz; }
+      else tabs[i].off = -1;
+    }
+    *s_total = run;
+  }
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    const int off = tabs[i].off;
+    if (off < 0) continue;
+    const int r = objs[i].r, sz = 2 * r * r + 1;
+    const double sigma = (double)(2 * r + 1) / 6.0;
+    const double den = 2.0 * sigma * sigma;
+    for (int d2 = threadIdx.x; d2 < sz; d2 += blockDim.x) tab[off + d2] = (float)exp(-(double)d2 / den);
+  }
+  __syncthreads();
+}
+
+// targets of the 4 pixels (x..x+3, y): objects are first rejected by row, then by column
+__device__ __forceinline__ float4 target_at4(const Obj *objs, const ObjTab *tabs, const float *tab, int n, int x, int y) {
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const int r = objs[i].r, dy = y - objs[i].y;
+    if (dy < -r || dy > r) continue;
+    const int dx0 = x - objs[i].x;
+    if (dx0 > r || dx0 + 3 < -r) continue;
+    const int off = tabs[i].off, dy2 = dy * dy;
+#define CNB_TAP(G, J)                                                                              \
+    {                                                                                              \
+      const int dx = dx0 + (J);                                                                    \
+      if (dx >= -r && dx <= r) G = fmaxf(G, (off >= 0) ? tab[off + dx * dx + dy2] : gauss_value(dx, dy, r)); \
+    }
+    CNB_TAP(g0, 0) CNB_TAP(g1, 1) CNB_TAP(g2, 2) CNB_TAP(g3, 3)
+#undef CNB_TAP
+  }
+  return make_float4(g0, g1, g2, g3);
+}
+__device__ __forceinline__ float target_at(const Obj *objs, const ObjTab *tabs, const float *tab, int n, int x, int y) {
   float g = 0.0f;
   for (int i = 0; i < n; ++i) {
     const int dx = x - objs[i].x, dy = y - objs[i].y, r = objs[i].r;
-    if (dx >= -r && dx <= r && dy >= -r && dy <= r) g = fmaxf(g, gauss_value(dx, dy, r));
+    if (dx >= -r && dx <= r && dy >= -r && dy <= r) {
+      const int off = tabs[i].off;
+      g = fmaxf(g, (off >= 0) ? tab[off + dx * dx + dy * dy] : gauss_value(dx, dy, r));
+    }
   }
   return g;
 }
@@ -204,9 +256,12 @@ __global__ void __launch_bounds__(FOCAL_THREADS) k_focal_splat(const float *__re
                                                                float *__restrict__ grad, float *__restrict__ hm,
                                                                FocalAcc *acc, float *out2) {
   __shared__ Obj s_obj[MAX_OBJ_PER_PLANE];
-  __shared__ int s_n;
+  __shared__ ObjTab s_tab[MAX_OBJ_PER_PLANE];
+  __shared__ float s_gauss[GAUSS_TAB_FLOATS];
+  __shared__ int s_n, s_total;
   const int b = blockIdx.x / C, c = blockIdx.x - b * C;
   const int nobj = gather_objects(cls, cx, cy, rad, valid, b, M, c, H, W, s_obj, &s_n);
+  if (nobj) build_tables(s_obj, nobj, s_tab, s_gauss, &s_total);
   const long long base = (long long)blockIdx.x * H * W;
   float inv_norm = 0.0f;
   if (!WRITE_HM) {
@@ -220,10 +275,7 @@ __global__ void __launch_bounds__(FOCAL_THREADS) k_focal_splat(const float *__re
     for (int i = threadIdx.x; i < HW / 4; i += blockDim.x) {
       const int y = (i * 4) / W, x = (i * 4) - y * W;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (nobj) {
-        g.x = target_at(s_obj, nobj, x, y); g.y = target_at(s_obj, nobj, x + 1, y);
-        g.z = target_at(s_obj, nobj, x + 2, y); g.w = target_at(s_obj, nobj, x + 3, y);
-      }
+      if (nobj) g = target_at4(s_obj, s_tab, s_gauss, nobj, x, y);
       if (WRITE_HM) {
         reinterpret_cast<float4 *>(hm + base)[i] = g;
       } else {
@@ -238,7 +290,7 @@ __global__ void __launch_bounds__(FOCAL_THREADS) k_focal_splat(const float *__re
   } else {
     for (int i = threadIdx.x; i < HW; i += blockDim.x) {
       const int y = i / W, x = i - y * W;
-      const float g = nobj ? target_at(s_obj, nobj, x, y) : 0.0f;
+      const float g = nobj ? target_at(s_obj, s_tab, s_gauss, nobj, x, y) : 0.0f;
       if (WRITE_HM) {
         hm[base + i] = g;
       } else {
@@ -351,6 +403,8 @@ int cnb_splat_gaussian(const int32_t *obj_cls, const int32_t *obj_cx, const int3
   CNB_REQUIRE(obj_cls && obj_cx && obj_cy && obj_radius && obj_valid && hm, CNB_EINVAL,
               "cnb_splat_gaussian: null pointer");
   CNB_REQUIRE(b > 0 && m > 0 && c > 0 && h > 0 && w > 0, CNB_EINVAL, "cnb_splat_gaussian: non-positive dimension");
+  CNB_REQUIRE(m <= MAX_OBJ_PER_PLANE, CNB_EUNSUPPORTED, "cnb_splat_gaussian: at most %d objects per image (got %d)",
+              MAX_OBJ_PER_PLANE, m);
   k_focal_splat<false, true><<<b * c, FOCAL_THREADS, 0, (cudaStream_t)stream_>>>(
       nullptr, obj_cls, obj_cx, obj_cy, obj_radius, obj_valid, m, c, h, w, 0.0f, nullptr, hm, nullptr, nullptr);
   CNB_CHECK_LAUNCH("cnb_splat_gaussian");
@@ -365,6 +419,8 @@ int cnb_focal_splat_loss(const float *pred, const int32_t *obj_cls, const int32_
   CNB_REQUIRE(pred && obj_cls && obj_cx && obj_cy && obj_radius && obj_valid && out2 && workspace, CNB_EINVAL,
               "cnb_focal_splat_loss: null pointer");
   CNB_REQUIRE(b > 0 && m > 0 && c > 0 && h > 0 && w > 0, CNB_EINVAL, "cnb_focal_splat_loss: non-positive dimension");
+  CNB_REQUIRE(m <= MAX_OBJ_PER_PLANE, CNB_EUNSUPPORTED, "cnb_focal_splat_loss: at most %d objects per image (got %d)",
+              MAX_OBJ_PER_PLANE, m);
   CNB_REQUIRE(workspace_bytes >= sizeof(FocalAcc), CNB_EWORKSPACE, "cnb_focal_splat_loss: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
   FocalAcc *acc = reinterpret_cast<FocalAcc *>(workspace);

@@ -79,6 +79,11 @@ PYBIND11_MODULE(_C, m) {
   m.def("sigmoid", [](P x, P out, long long n, P stream) {
     check(cnb_sigmoid(ptr<const float>(x), ptr<float>(out), n, ptr<void>(stream)), "cnb_sigmoid");
   });
+  m.def("flip_merge", [](P src, P dst, int n, int c, int h, int w, int sig, P perm, P sign, P stream) {
+    check(cnb_flip_merge(ptr<const float>(src), ptr<float>(dst), n, c, h, w, sig, ptr<const int32_t>(perm),
+                         ptr<const float>(sign), ptr<void>(stream)),
+          "cnb_flip_merge");
+  });
   m.def("psroi_pooling_forward", [](P data, P rois, P trans, P out, P cnt, int b, int c, int h, int w, int n, int ct,
                                     int no_trans, float scale, int od, int gs, int ps, int part, int spp, float tstd,
                                     P stream) {
@@ -195,6 +200,15 @@ PYBIND11_MODULE(_C, m) {
                                      ptr<const void>(wt), ptr<const float>(bias), ptr<float>(output), b, cin, h, w,
                                      cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, ptr<void>(ws), wsb, ptr<void>(stream)),
           "cnb_dcnv2_forward_prepared");
+  });
+  m.def("dcnv2_forward_fused", [](P input, int nhwc, P om, P wt, P bias, P sc, P sh_, int relu, P output, int b, int cin,
+                                  int h, int w, int cout, int kh, int kw, int stride, int pad, int dil, int dg, P ws,
+                                  size_t wsb, P stream) {
+    check(cnb_dcnv2_forward_fused(ptr<const float>(input), nhwc, ptr<const float>(om), ptr<const void>(wt),
+                                  ptr<const float>(bias), ptr<const float>(sc), ptr<const float>(sh_), relu,
+                                  ptr<float>(output), b, cin, h, w, cout, kh, kw, stride, pad, dil, dg, ptr<void>(ws),
+                                  wsb, ptr<void>(stream)),
+          "cnb_dcnv2_forward_fused");
   });
   m.def("dcnv2_backward", [](P input, P offset, P mask, P weight, P gout, P gin, P goff, P gmask, P gw, P gb, int b,
                              int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,

@@ -810,7 +810,7 @@ enum { SW_BOTH = 0, SW_HIST = 1, SW_KEYS = 2 };  // what a qualifying pixel upda
 __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl, int b, int nslots, bool local,
                              int n_local, const u64 *__restrict__ cand, const int *__restrict__ cand_cnt,
                              const uint32_t *__restrict__ cand_thr, const FinalizeOut &out, u64 *sbuf, int *s_fcnt,
-                             int *s_tmp, u64 *s_red) {
+                             int *s_tmp, u64 *s_red, int *fine, int *coarse) {
   const int tid = threadIdx.x, K = pl.K, cap = pl.seg_cap;
   int total;
   bool sorted = false;
@@ -834,7 +834,43 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
     __syncthreads();
     // every segment threshold is a valid lower bound of the image's K-th best score (the K-th best of a
     // subset never exceeds the K-th best of the whole), hence so is the largest of them
-    const uint32_t T = (uint32_t)s_tmp[1];
+    uint32_t T = (uint32_t)s_tmp[1];
+    if (nslots > 8) {
+      // small batches: an image is spread over many one-plane segments whose thresholds are all alike, so the
+      // cut above still leaves thousands of keys.  One histogram pass over the (L2-resident) keys gives the
+      // K-th best of the union to 1/128 octave; the second pass then keeps ~1.0-1.3 K keys.
+      for (int i = tid; i < SEL_HIST_FINE + SEL_HIST_COARSE; i += SEL_THREADS) fine[i] = 0;
+      __syncthreads();
+      for (int it0 = 0; it0 < items; it0 += 4 * SEL_THREADS) {
+        u64 kk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int it = it0 + q * SEL_THREADS + tid;
+          kk[q] = (it < items) ? __ldcg(keys + it) : 0ull;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int it = it0 + q * SEL_THREADS + tid;
+          if (it < items) {
+            const int slot = it / cap, j = it - slot * cap;
+            if (j < s_fcnt[slot] && key_bits(kk[q]) >= T) atomicAdd(&fine[hist_bin(key_bits(kk[q]))], 1);
+          }
+        }
+      }
+      __syncthreads();
+      {
+        const int warp = tid >> 5, lane = tid & 31;
+        int sum = fine[warp * 64 + lane] + fine[warp * 64 + 32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) coarse[warp] = sum;
+      }
+      __syncthreads();
+      if (tid < 32) update_threshold(fine, coarse, tid, K, reinterpret_cast<uint32_t *>(&s_tmp[3]));
+      __syncthreads();
+      T = max(T, (uint32_t)s_tmp[3]);
+      __syncthreads();
+    }
     auto take = [&](u64 key, int it) {
       const int slot = it / cap, j = it - slot * cap;
       if (j < s_fcnt[slot] && key_bits(key) >= T) {
@@ -929,6 +965,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   float *s_tl = reinterpret_cast<float *>(s_cnt + 5);        // LOGITS: logit-space lower bound of *s_thr
   __shared__ int s_arr[SEL_STAGES];                          // warps done with the stage (last one re-arms it)
   __shared__ int s_flag[4];                                  // compaction rendezvous requested for unit (u & 3)
+  __shared__ uint32_t s_exact;                               // score bits of an exact K-th best (0: none yet)
   __shared__ int s_tmp[32];
   __shared__ u64 s_red[32];
   static_assert(SEL_MASK_WORDS >= SEL_MAX_CTA, "s_fcnt must hold one count per candidate segment");
@@ -959,11 +996,16 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
     *s_thr = 0u;
     *s_tl = CNB_NEG_INF;
+    s_exact = 0u;
   };
   // one warp: refresh the histogram threshold (and its logit-space image)
   auto refresh_thr = [&]() {
     update_threshold(fine, coarse, lane, K, s_thr);
-    if (LOGITS && lane == 0) *s_tl = logit_lower_bound(*s_thr);
+    if (lane == 0) {
+      const uint32_t ex = *(volatile uint32_t *)&s_exact;      // exact K-th best of an earlier sort-prune, if any
+      if (ex > *s_thr) *s_thr = ex;
+      if (LOGITS) *s_tl = logit_lower_bound(*s_thr);
+    }
   };
 
   if (tid == 0) {
@@ -1037,6 +1079,17 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
         if (mine[j] != 0ull && key_bits(mine[j]) >= tb) buf[atomicAdd(&s_cnt[0], 1)] = mine[j];
     }
     __syncthreads();
+    if (fits && s_cnt[0] > SEL_CAP / 2) {
+      // the histogram cannot separate them (many candidates inside one 1/128-octave bin: flat noise floors,
+      // plateaus): cut exactly -- sort, keep the K best, and raise the threshold to the K-th best score itself
+      const u64 kth = cta_prune(buf, s_cnt, K);
+      if (tid == 0 && kth != 0ull) {
+        s_exact = max(s_exact, key_bits(kth));
+        *s_thr = max(*s_thr, s_exact);
+        if (LOGITS) *s_tl = logit_lower_bound(*s_thr);
+      }
+      __syncthreads();
+    }
   };
 
   // ---- CTA-wide flush of image `img` (all threads; called at image boundaries only)
@@ -1086,7 +1139,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     const int i1 = (img == img_hi) ? i1_last : me;
     if (i0 == i1) {
       // the image lies entirely in this CTA: no segment, no ticket -- finalize from shared memory
-      finalize_hot(src, pl, img, 1, true, n_out, cand, cand_cnt, cand_thr, fout, buf, s_fcnt, s_tmp, s_red);
+      finalize_hot(src, pl, img, 1, true, n_out, cand, cand_cnt, cand_thr, fout, buf, s_fcnt, s_tmp, s_red, fine, coarse);
       clear_hist();
       if (tid == 0) clear_scalars();
       __syncthreads();
@@ -1109,7 +1162,9 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     __syncthreads();
     if (s_cnt[2]) {  // every segment of this image is in global memory: merge + emit here
       __threadfence();
-      finalize_hot(src, pl, img, i1 - i0 + 1, false, 0, cand, cand_cnt, cand_thr, fout, buf, s_fcnt, s_tmp, s_red);
+      finalize_hot(src, pl, img, i1 - i0 + 1, false, 0, cand, cand_cnt, cand_thr, fout, buf, s_fcnt, s_tmp, s_red, fine,
+                   coarse);
+      clear_hist();   // the many-segment finalize borrows the histogram
     }
     if (tid == 0) clear_scalars();
     __syncthreads();

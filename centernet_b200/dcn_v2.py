@@ -7,7 +7,7 @@ import torch
 from torch import nn
 from torch.nn.modules.utils import _pair
 
-from .dcn_v2_func import DCNv2Function, DCNv2PoolingFunction
+from .dcn_v2_func import DCNv2Function, DCNv2PoolingFunction, dcn_fused_inference
 
 
 class DCNv2(nn.Module):
@@ -56,6 +56,10 @@ class DCN(DCNv2):
 
     def forward(self, input):
         out = self.conv_offset_mask(input)
+        if input.is_cuda and not torch.is_grad_enabled() and self.kernel_size[0] * self.kernel_size[1] <= 9:
+            # inference: chunk / cat / sigmoid (the three lines below) run inside the DCN kernel's sampler
+            return dcn_fused_inference(input, out, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                                       self.deformable_groups)
         o1, o2, mask = torch.chunk(out, 3, dim=1)
         offset = torch.cat((o1, o2), dim=1)
         mask = torch.sigmoid(mask)
@@ -115,3 +119,39 @@ class DCNPooling(DCNv2Pooling):
         offset = self.offset_fc(x.view(n, -1)).view(n, 2, self.pooled_size, self.pooled_size)
         mask = self.mask_fc(x.view(n, -1)).view(n, 1, self.pooled_size, self.pooled_size)
         return self.func(data, rois, offset) * mask
+
+
+# ------------------------------------------------------------------ N3: DCN + BatchNorm + ReLU (pose_dla_dcn.py:345-357)
+def fold_bn(bn):
+    """Inference BatchNorm as y = scale * x + shift (float64 fold, fp32 result)."""
+    var = bn.running_var.double()
+    scale = (bn.weight.double() if bn.affine else torch.ones_like(var)) / torch.sqrt(var + bn.eps)
+    shift = (bn.bias.double() if bn.affine else torch.zeros_like(var)) - bn.running_mean.double() * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def fuse_dcn_bn_relu(model):
+    """Rewires every `DeformConv`-shaped module of `model` (attributes `conv`: DCN and `actf`:
+    Sequential(BatchNorm2d, ReLU), pose_dla_dcn.py:345-357) so that in eval mode under no_grad the BatchNorm and
+    the ReLU run in the DCN kernel's epilogue (no extra passes over the activation).  Training / grad mode keeps
+    the original three-module path.  Returns the number of modules fused."""
+    n = 0
+    for m in model.modules():
+        conv, actf = getattr(m, "conv", None), getattr(m, "actf", None)
+        if not (isinstance(conv, DCN) and isinstance(actf, nn.Sequential) and len(actf) == 2 and
+                isinstance(actf[0], nn.BatchNorm2d) and isinstance(actf[1], nn.ReLU)):
+            continue
+        orig = m.forward
+
+        def fused(x, _m=m, _orig=orig):
+            c, bn = _m.conv, _m.actf[0]
+            if _m.training or torch.is_grad_enabled() or not x.is_cuda or not bn.track_running_stats:
+                return _orig(x)
+            scale, shift = fold_bn(bn)
+            om = c.conv_offset_mask(x)
+            return dcn_fused_inference(x, om, c.weight, c.bias, c.stride, c.padding, c.dilation, c.deformable_groups,
+                                       bn_scale=scale, bn_shift=shift, relu=True)
+
+        m.forward = fused
+        n += 1
+    return n

@@ -112,6 +112,39 @@ class _DCNv2(Function):
         return gx, goff, gmsk, gw, gb, None, None, None, None
 
 
+def dcn_fused_inference(input, offset_mask, weight, bias, stride, padding, dilation, deformable_groups,
+                        bn_scale=None, bn_shift=None, relu=False):
+    """Inference form of the whole DCN module around ONE kernel (cnb_dcnv2_forward_fused): `offset_mask` is the raw
+    conv_offset_mask output (chunk / cat / sigmoid of dcn_v2.py:64-70 happen inside the sampler), bn_scale /
+    bn_shift / relu the folded BatchNorm + ReLU that follow the DCN in DeformConv (pose_dla_dcn.py:345-357).
+    No autograd (use DCNv2Function for training)."""
+    if not input.is_cuda:
+        raise NotImplementedError
+    n, cin, h, wd = [int(v) for v in input.shape]
+    cout, cin_w, kh, kw = [int(v) for v in weight.shape]
+    if cin_w != cin:
+        raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (cin, cin_w))
+    if kh * kw > 9:
+        raise NotImplementedError("dcn_fused_inference: at most 9 taps")
+    ho, wo = _out_hw(h, wd, kh, kw, stride, padding, dilation)
+    om = f32c(offset_mask)
+    if tuple(om.shape) != (n, 3 * kh * kw * deformable_groups, ho, wo):
+        raise RuntimeError("dcn_fused_inference: offset_mask must be [%d, %d, %d, %d]" % (n, 3 * kh * kw * deformable_groups, ho, wo))
+    nhwc = (cin // deformable_groups) % 32 == 0 and input.dtype == torch.float32 and \
+        input.is_contiguous(memory_format=torch.channels_last) and not input.is_contiguous()
+    xin = input if nhwc else f32c(input)
+    wt = _weight_tiles(weight, deformable_groups)
+    out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=input.device)
+    ws = workspace(C.dcnv2_prepared_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding, dilation,
+                                                    deformable_groups), input.device)
+    b = f32c(bias)
+    sc, sh = f32c(bn_scale), f32c(bn_shift)
+    C.dcnv2_forward_fused(ptr(xin), int(nhwc), ptr(om), ptr(wt), ptr(b), ptr(sc), ptr(sh), int(bool(relu)), ptr(out),
+                          n, cin, h, wd, cout, kh, kw, stride, padding, dilation, deformable_groups, ptr(ws),
+                          ws.numel(), stream_ptr(om))
+    return out
+
+
 class DCNv2Function(object):
     """Callable instance, same constructor as the reference's old-style Function."""
 

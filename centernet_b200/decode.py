@@ -163,6 +163,56 @@ def sigmoid(x):
     return out
 
 
+# ------------------------------------------------------------------ flip test (detectors/*.py), N1
+def flip_merge(x, sigmoid=False, flip_idx=None, offsets=False):
+    """(f(x[:n]) + flip(f(x[n:]))) / 2 for a batch x [2n, C, H, W] = n images followed by their mirrored copies
+    (base_detector.py:63-64).  flip: flip_tensor; with `flip_idx` the joint channels are swapped as in flip_lr
+    (models/utils.py:33-39), with `offsets` as in flip_lr_off (:41-50: C = 2 x joints, x offsets negated).
+    One kernel, no host round trip (the reference's flip_lr / flip_lr_off go through numpy)."""
+    require_cuda(x, what="flip_merge")
+    x = f32c(x)
+    b2, c, h, w = _dims(x)
+    if b2 % 2:
+        raise RuntimeError("flip_merge: batch must hold image / mirrored-image pairs")
+    n = b2 // 2
+    perm = sign = None
+    if flip_idx is not None:
+        if offsets:
+            j = c // 2
+            p = list(range(j))
+            for a, b_ in flip_idx:
+                p[a], p[b_] = p[b_], p[a]
+            perm = torch.tensor([2 * p[ch // 2] + (ch & 1) for ch in range(c)], dtype=torch.int32, device=x.device)
+            sign = torch.tensor([-1.0 if (ch & 1) == 0 else 1.0 for ch in range(c)], dtype=torch.float32, device=x.device)
+        else:
+            p = list(range(c))
+            for a, b_ in flip_idx:
+                p[a], p[b_] = p[b_], p[a]
+            perm = torch.tensor(p, dtype=torch.int32, device=x.device)
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    C.flip_merge(ptr(x), ptr(out), n, c, h, w, int(bool(sigmoid)), ptr(perm), ptr(sign), stream_ptr(x))
+    return out
+
+
+def ctdet_decode_flip_from_logits(hm, wh, reg=None, cat_spec_wh=False, K=100):
+    """detectors/ctdet.py:30-45 with --flip_test: hm/wh/reg [2n, ...] (images then mirrored images) ->
+    dets [n, K, 6].  Two launches (merge of hm + wh, fused decode) instead of ~10 ATen ops + the decode."""
+    heat = flip_merge(hm, sigmoid=True)
+    whm = flip_merge(wh)
+    n = heat.shape[0]
+    return ctdet_decode(heat, whm, reg=None if reg is None else reg[:n], cat_spec_wh=cat_spec_wh, K=K)
+
+
+def multi_pose_decode_flip_from_logits(hm, wh, hps, reg=None, hm_hp=None, hp_offset=None, flip_idx=(), K=100):
+    """detectors/multi_pose.py:29-55 with --flip_test (hm and hm_hp given as logits)."""
+    heat = flip_merge(hm, sigmoid=True)
+    n = heat.shape[0]
+    hm_hp_m = None if hm_hp is None else flip_merge(hm_hp, sigmoid=True, flip_idx=flip_idx)
+    return multi_pose_decode(heat, flip_merge(wh), flip_merge(hps, flip_idx=flip_idx, offsets=True),
+                             reg=None if reg is None else reg[:n], hm_hp=hm_hp_m,
+                             hp_offset=None if hp_offset is None else hp_offset[:n], K=K)
+
+
 # ------------------------------------------------------------------ decode.py:426-462
 def ddd_decode(heat, rot, depth, dim, wh=None, reg=None, K=40):
     require_cuda(heat, rot, depth, dim, wh, reg, what="ddd_decode")

@@ -137,8 +137,8 @@ def ctdet_merge_device(dets_per_scale, metas, num_classes, max_per_image=100, nm
         m = metas[k]
         t = transform_dets(dets_per_scale[k], m["c"], m["s"], m["out_height"], m["out_width"], ((0, 2), (0, 0)))
         sc = float(m.get("scale", 1.0))
-        if sc != 1.0:
-            t[:, :, :4] /= sc
+        if sc != 1.0:   # a tensor divisor: torch turns division by a Python scalar into a multiplication by 1/scale
+            t[:, :, :4] /= torch.tensor(sc, dtype=torch.float32, device=t.device)
         parts.append(t)
     allp = torch.cat(parts, dim=1).contiguous()          # scale-major, like np.concatenate over `detections`
     b, n, _ = [int(v) for v in allp.shape]

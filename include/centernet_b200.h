@@ -111,6 +111,15 @@ int cnb_ctdet_decode_logits(const float *hm_logits, const float *wh, const float
  * fused path applies to its candidates (exposed so tests can pin it against torch and prove it monotone). */
 int cnb_sigmoid(const float *x, float *out, long long n, void *stream);
 
+/* ------------------------------------------- N1: flip-test merge of the heads
+ * detectors/ctdet.py:34-37 and detectors/multi_pose.py:43-51.  src [2n,c,h,w]:
+ * n images followed by their horizontally flipped copies; dst [n,c,h,w] =
+ * (f(src[i,ch]) + sign[ch] * f(flip_w(src[n+i, perm[ch]]))) / 2, f = sigmoid when
+ * apply_sigmoid.  perm/sign NULL = flip_tensor (models/utils.py:28-29); perm =
+ * joint swap for flip_lr (:33-39); perm + sign for flip_lr_off (:41-50). */
+int cnb_flip_merge(const float *src, float *dst, int n, int c, int h, int w, int apply_sigmoid,
+                   const int32_t *perm, const float *sign, void *stream);
+
 /* ------------------------------------------------------------ A9: ddd_decode
  * models/decode.py:426-462.  rot [b,8,h,w], depth [b,1,h,w], dim [b,3,h,w],
  * wh/reg [b,2,h,w] or NULL -> dets [b,k,18] (16 when wh == NULL). */
@@ -224,6 +233,18 @@ int cnb_dcnv2_forward_prepared(const float *input, int input_channels_last, cons
                                int stride_h, int stride_w, int pad_h, int pad_w,
                                int dil_h, int dil_w, int deformable_groups,
                                void *workspace, size_t workspace_bytes, void *stream);
+/* N3 (inference): the DCN module with its prologue and epilogue fused around the tensor-core kernel.
+ * offset_mask is the RAW output of DCN.conv_offset_mask, [b, 3*kh*kw*dg, ho, wo]: its first two thirds are
+ * read as the offsets and the sigmoid of its last third as the mask inside the sampler (dcn_v2.py:64-70:
+ * chunk, cat and sigmoid disappear); bn_scale / bn_shift (nullable, [cout]) are the folded inference
+ * BatchNorm that follows the DCN in DeformConv and relu its activation (pose_dla_dcn.py:345-357):
+ * y = relu(bn_scale * (dcn + bias) + bn_shift).  Workspace as cnb_dcnv2_forward_prepared. */
+int cnb_dcnv2_forward_fused(const float *input, int input_channels_last, const float *offset_mask,
+                            const void *wtiles, const float *bias, const float *bn_scale,
+                            const float *bn_shift, int relu, float *output,
+                            int b, int cin, int h, int w, int cout, int kh, int kw,
+                            int stride, int pad, int dil, int deformable_groups,
+                            void *workspace, size_t workspace_bytes, void *stream);
 int cnb_dcnv2_backward(const float *input, const float *offset, const float *mask,
                        const float *weight, const float *grad_output,
                        float *grad_input, float *grad_offset, float *grad_mask,

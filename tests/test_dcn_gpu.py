@@ -93,3 +93,45 @@ def test_dcn_module_and_state_dict_names():
     assert dcn.weight.grad is not None and dcn.conv_offset_mask.weight.grad is not None
     with pytest.raises(NotImplementedError):
         dcn.cpu()(torch.randn(1, 16, 8, 8))
+
+
+def test_fused_inference_paths():
+    """N3: conv_offset_mask glue (chunk / cat / sigmoid) fused into the sampler, BatchNorm + ReLU into the epilogue;
+    channels_last activations sampled in place; cached weight tiles follow in-place weight updates."""
+    from centernet_b200.dcn_v2 import DCN, fuse_dcn_bn_relu
+    from torch import nn
+    torch.manual_seed(0)
+
+    class DeformConv(nn.Module):          # shape of pose_dla_dcn.py:345-357
+        def __init__(self, chi, cho):
+            super().__init__()
+            self.actf = nn.Sequential(nn.BatchNorm2d(cho), nn.ReLU(inplace=True))
+            self.conv = DCN(chi, cho, kernel_size=(3, 3), stride=1, padding=1, dilation=1, deformable_groups=1)
+
+        def forward(self, x):
+            return self.actf(self.conv(x))
+
+    for chi, cho, hw in ((64, 64, 40), (128, 256, 16), (24, 40, 9)):
+        m = DeformConv(chi, cho).cuda()
+        m.conv.conv_offset_mask.weight.data.normal_(0, 0.02); m.conv.conv_offset_mask.bias.data.normal_(0, 0.5)
+        m.actf[0].running_mean.normal_(0, 0.3); m.actf[0].running_var.uniform_(0.5, 2.0)
+        m.actf[0].weight.data.uniform_(0.5, 1.5); m.actf[0].bias.data.normal_(0, 0.2)
+        m.eval()
+        x = torch.randn(2, chi, hw, hw, device="cuda")
+        with torch.enable_grad():
+            want_dcn = m.conv(x)                       # unfused three-op path (grad mode)
+            want = m.actf(want_dcn.clone())
+        with torch.no_grad():
+            got_dcn = m.conv(x)                        # fused prologue
+            assert (got_dcn - want_dcn).abs().max().item() <= 1e-4
+            assert fuse_dcn_bn_relu(m) == 1
+            got = m(x)
+            assert (got - want).abs().max().item() <= 2e-4
+            if chi % 32 == 0:
+                xcl = x.contiguous(memory_format=torch.channels_last)
+                assert (m(xcl) - want).abs().max().item() <= 2e-4
+            # in-place weight update must invalidate the cached tiles
+            m.conv.weight.data.mul_(0.5)
+            with torch.enable_grad():
+                want2 = m.actf(m.conv(x))
+            assert (m(x) - want2).abs().max().item() <= 2e-4

@@ -107,3 +107,24 @@ def test_logits_cat_spec_and_misaligned():
     mis = buf[1:].view(B, C, H, W)
     assert mis.data_ptr() % 16 != 0
     _check(mis, wh[:, :2].contiguous(), reg, K)
+
+
+def test_flip_merge_matches_reference_ops():
+    """N1: flip-test merges (detectors/ctdet.py:34-37, multi_pose.py:43-51) against the reference's op sequence
+    (sigmoid_, flip_tensor / flip_lr / flip_lr_off of models/utils.py, add, divide), bit for bit."""
+    from centernet_b200 import decode as D, utils as U
+    g = torch.Generator().manual_seed(5)
+    flip_idx = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
+    hm = (torch.randn(4, 6, 12, 20, generator=g) * 3).cuda()
+    hps = torch.randn(4, 34, 12, 20, generator=g).cuda()
+    hm_hp = (torch.randn(4, 17, 12, 20, generator=g) * 2).cuda()
+    s = torch.sigmoid(hm)
+    assert torch.equal(D.flip_merge(hm, sigmoid=True), (s[0:2] + U.flip_tensor(s[2:4])) / 2)
+    assert torch.equal(D.flip_merge(hps), (hps[0:2] + U.flip_tensor(hps[2:4])) / 2)
+    assert torch.equal(D.flip_merge(hps, flip_idx=flip_idx, offsets=True), (hps[0:2] + U.flip_lr_off(hps[2:4], flip_idx)) / 2)
+    sp = torch.sigmoid(hm_hp)
+    assert torch.equal(D.flip_merge(hm_hp, sigmoid=True, flip_idx=flip_idx), (sp[0:2] + U.flip_lr(sp[2:4], flip_idx)) / 2)
+    # whole flip-test decode == reference composition
+    wh = (torch.rand(4, 2, 12, 20, generator=g) * 9).cuda(); reg = torch.rand(4, 2, 12, 20, generator=g).cuda()
+    want = D.ctdet_decode((s[0:2] + U.flip_tensor(s[2:4])) / 2, (wh[0:2] + U.flip_tensor(wh[2:4])) / 2, reg=reg[0:2], K=15)
+    assert torch.equal(D.ctdet_decode_flip_from_logits(hm, wh, reg=reg, K=15), want)
