@@ -46,26 +46,52 @@ def workload_config(world):
     }
 
 
+def _nvml_handle(cuda_index):
+    """NVML handle of CUDA device `cuda_index`.  NVML enumerates every GPU of the box while CUDA sees only the
+    visible ones (CUDA_VISIBLE_DEVICES), so the two indices differ: match through the PCI bus id."""
+    import pynvml as nv
+    nv.nvmlInit()
+    p = torch.cuda.get_device_properties(cuda_index)
+    if all(hasattr(p, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+        bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        try:
+            return nv, nv.nvmlDeviceGetHandleByPciBusId(bus.encode()), bus
+        except Exception:
+            pass
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [v.strip() for v in vis.split(",") if v.strip()]
+    if cuda_index < len(ids):
+        v = ids[cuda_index]
+        try:
+            h = nv.nvmlDeviceGetHandleByUUID(v.encode()) if v.startswith("GPU-") else nv.nvmlDeviceGetHandleByIndex(int(v))
+            return nv, h, "visible:" + v
+        except Exception:
+            pass
+    return nv, nv.nvmlDeviceGetHandleByIndex(cuda_index), "index:%d" % cuda_index
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this rank (and the pinned host buffers it allocates afterwards, first touch) to the NUMA node its
     GPU hangs off: at N=8 the eight H2D streams otherwise fight over one socket's memory controllers.
     Returns a short description for the JSON line."""
     try:
-        import pynvml as nv
-        nv.nvmlInit()
-        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        nv, h, how = _nvml_handle(index)
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
         bus = bus.decode() if isinstance(bus, bytes) else bus
         dom, rest = bus.split(":", 1)
         path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
         node = int(open(path).read().strip())
         if node < 0:
-            return "numa_node unknown (single node)"
+            return "numa_node unknown (single node), gpu %s" % bus
         cpus = []
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.extend(range(int(a), int(b or a) + 1))
-        os.sched_setaffinity(0, cpus)
-        return "bound to NUMA node %d (%d cpus)" % (node, len(cpus))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "not bound (node %d has no allowed cpu), gpu %s" % (node, bus)
+        os.sched_setaffinity(0, allowed)
+        return "gpu %s (%s) -> NUMA node %d, %d cpus" % (bus, how, node, len(allowed))
     except Exception as e:
         return "not bound (%s)" % type(e).__name__
 
@@ -91,9 +117,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            nv, h, _ = _nvml_handle(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {
                 getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
@@ -308,6 +332,16 @@ def main():
     e2e_value = None
     if args.e2e_steps > 0:
         host = [tuple(x.cpu().pin_memory() for x in batches[i]) for i in range(2)]
+        # what the link gives a plain pinned copy of the same buffers right now (shared hosts vary a lot)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        batches[0][0].copy_(host[0][0], non_blocking=True)
+        torch.cuda.synchronize()
+        p0.record()
+        for _ in range(3):
+            batches[0][0].copy_(host[0][0], non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize()
+        h2d_probe = 3 * host[0][0].numel() * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
         for i in range(2):
             D.ctdet_decode_from_host(*host[i % 2][:2], reg=host[i % 2][2], K=K)
         barrier()
@@ -365,7 +399,8 @@ def main():
                          "alg_bytes_per_launch": ALG_BYTES_PER_IMAGE * B_PER_GPU},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps,
-                    "h2d_gbs_per_rank": h2d_gbs_per_rank if args.e2e_steps > 0 else None, "host_binding": numa,
+                    "h2d_gbs_per_rank": h2d_gbs_per_rank if args.e2e_steps > 0 else None,
+                    "h2d_probe_gbs": round(h2d_probe, 2) if args.e2e_steps > 0 else None, "host_binding": numa,
                     "bound_by": "PCIe Gen5 x16 host->device copy of the fp32 heat/wh/reg batch (352 MB per step, "
                                 "pinned, chunked and overlapped with the decode); the decode itself is ~1% of it"},
             "gpu_launches": int(launches),

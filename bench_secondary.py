@@ -196,6 +196,17 @@ def run(dev, batches, K=100, steps=20):
                     ref_gpu.dcn_v2_backward(x, off, msk, w, bias, go)
                 r["reference_gpu_fwd_bwd_ms"] = round(timeit(rfb, 3, 1), 5)
                 r["reference_gpu"] = "oracle/_ref: the reference's dcn_v2_im2col_cuda.cu compiled unmodified + cuBLAS SGEMM"
+            try:   # third-party bar of BASELINE.md section 2(c): the same algorithm as shipped by torchvision
+                from torchvision.ops import deform_conv2d
+                r["torchvision_fwd_ms"] = round(timeit(lambda: deform_conv2d(x, off, w, bias, padding=1, mask=msk), 5, 2), 5)
+
+                def tvfb():
+                    for t in leaves:
+                        t.grad = None
+                    deform_conv2d(leaves[0], leaves[1], leaves[3], leaves[4], padding=1, mask=leaves[2]).sum().backward()
+                r["torchvision_fwd_bwd_ms"] = round(timeit(tvfb, 3, 1), 5)
+            except Exception:
+                pass
             return r
         guarded("dcnv2_b%d_%dx%d_%dto%d" % (b, hh, hh, ci, co), dcn)
 

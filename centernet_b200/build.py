@@ -19,7 +19,7 @@ LIB = os.path.join(LIBDIR, "libcenternet_b200.so")
 EXT = os.path.join(HERE, "_C" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-cudart", "static"] + os.environ.get("CNB_NVCC_DEFINES", "").split()
 
 
 def _newer(target, sources):

@@ -26,6 +26,7 @@
 // Non-positive scores (zero fillers, negative peaks) only matter when an image has < K
 // positive peaks; finalize handles that exactly with an ordered rescan (rare slow path).
 #include "select.cuh"
+#include <stdlib.h>
 
 namespace cnb {
 
@@ -871,16 +872,24 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
       T = max(T, (uint32_t)s_tmp[3]);
       __syncthreads();
     }
-    auto take = [&](u64 key, int it) {
+    auto take = [&](u64 key, int it) {   // called by whole warps: one shared-memory atomic per warp, not per key
       const int slot = it / cap, j = it - slot * cap;
-      if (j < s_fcnt[slot] && key_bits(key) >= T) {
-        const int pos = atomicAdd(&s_tmp[0], 1);
-        if (pos < SEL_CAP) sbuf[pos] = key;
-        else s_tmp[2] = 1;
+      const bool ok = it < items && j < s_fcnt[slot] && key_bits(key) >= T;
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      if (bal) {
+        const int lane_ = tid & 31, leader = __ffs(bal) - 1;
+        int base_pos = 0;
+        if (lane_ == leader) base_pos = atomicAdd(&s_tmp[0], __popc(bal));
+        base_pos = __shfl_sync(0xffffffffu, base_pos, leader);
+        if (ok) {
+          const int pos = base_pos + __popc(bal & ((1u << lane_) - 1u));
+          if (pos < SEL_CAP) sbuf[pos] = key;
+          else s_tmp[2] = 1;
+        }
       }
     };
-    if (tid < items) take(k0, tid);
-    if (tid + SEL_THREADS < items) take(k1, tid + SEL_THREADS);
+    take(k0, tid);
+    take(k1, tid + SEL_THREADS);
     for (int it0 = 2 * SEL_THREADS; it0 < items; it0 += 4 * SEL_THREADS) {   // small batches: many slots
       u64 kk[4];
 #pragma unroll
@@ -889,10 +898,7 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
         kk[q] = (it < items) ? __ldcg(keys + it) : 0ull;
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int it = it0 + q * SEL_THREADS + tid;
-        if (it < items) take(kk[q], it);
-      }
+      for (int q = 0; q < 4; ++q) take(kk[q], it0 + q * SEL_THREADS + tid);
     }
     __syncthreads();
     total = s_tmp[0];
@@ -919,6 +925,35 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
     }
   }
   const u64 *res = sbuf;
+  if (!sorted && total > 256 && total <= SEL_CAP / 2) {
+    // too many for the rank sort: one more cut, by a histogram of the keys already in shared memory (the K-th
+    // best to 1/128 octave leaves ~1.0-1.3 K keys); far cheaper than a 512- or 1024-key bitonic sort
+    for (int i = tid; i < SEL_HIST_FINE + SEL_HIST_COARSE; i += SEL_THREADS) fine[i] = 0;
+    __syncthreads();
+    for (int t = tid; t < total; t += SEL_THREADS) atomicAdd(&fine[hist_bin(key_bits(sbuf[t]))], 1);
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      int sum = fine[warp * 64 + lane] + fine[warp * 64 + 32 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) coarse[warp] = sum;
+    }
+    if (tid == 0) s_tmp[0] = 0;
+    __syncthreads();
+    if (tid < 32) update_threshold(fine, coarse, tid, K, reinterpret_cast<uint32_t *>(&s_tmp[3]));
+    __syncthreads();
+    const uint32_t t2 = (uint32_t)s_tmp[3];
+    u64 *dst = sbuf + SEL_CAP / 2;
+    for (int t = tid; t < total; t += SEL_THREADS) {
+      const u64 key = sbuf[t];
+      if (key_bits(key) >= t2) dst[atomicAdd(&s_tmp[0], 1)] = key;
+    }
+    __syncthreads();
+    total = s_tmp[0];
+    for (int t = tid; t < total; t += SEL_THREADS) sbuf[t] = dst[t];
+    __syncthreads();
+  }
   if (!sorted) {
     if (total <= 256) {
       // few survivors: rank sort, 4 threads per key (every key counts the keys above it; keys are unique)
@@ -948,6 +983,15 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
   emit_rows<CtaGroup>(pl, b, res, out);
   __syncthreads();
 }
+
+#ifdef CNB_SELECT_STATS
+// tuning build only (tools/select_stats.py rebuilds the library with -DCNB_SELECT_STATS): per CTA
+// [total, wait, bootstrap, flush, finalize] cycles and [units, bootstraps, flushes, finalizes] counts
+__device__ unsigned long long g_select_stats[SEL_MAX_CTA][10];
+#define CNB_STAT(x) x
+#else
+#define CNB_STAT(x)
+#endif
 
 template <bool LOGITS>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
@@ -1026,6 +1070,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   if (tid == 64) s_tmp[27] = plan_cta_of_plane(pl, (long long)(img_hi + 1) * C - 1);
   __syncthreads();
   const int i0_first = s_tmp[26], i1_last = s_tmp[27];
+  CNB_STAT(if (tid == 0) { s_tmp[24] = 0; s_tmp[25] = 0; })
 
   // one qualifying pixel (any lane of any warp, concurrently)
   auto push = [&](float v, uint32_t flat, int mode) {
@@ -1056,8 +1101,10 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
   // ---- CTA-wide compaction of the key buffer against the current threshold (rendezvous, rare)
   auto compact = [&](int slot_idx) {
     __syncthreads();
-    if (warp == 0) refresh_thr();
-    __syncthreads();
+    if (slot_idx >= 0) {     // mid-stream rendezvous: bring the threshold up to date first (flush: already is)
+      if (warp == 0) refresh_thr();
+      __syncthreads();
+    }
     const uint32_t tb = *s_thr;
     const bool fits = s_cnt[0] <= SEL_CAP;       // read once here, while nobody modifies it
     const int cnt = min(s_cnt[0], SEL_CAP);
@@ -1162,9 +1209,12 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     __syncthreads();
     if (s_cnt[2]) {  // every segment of this image is in global memory: merge + emit here
       __threadfence();
+      CNB_STAT(const long long fq = clock64();)
+      CNB_STAT(if (tid == 0) { s_tmp[24] += 1; })
       finalize_hot(src, pl, img, i1 - i0 + 1, false, 0, cand, cand_cnt, cand_thr, fout, buf, s_fcnt, s_tmp, s_red, fine,
                    coarse);
       clear_hist();   // the many-segment finalize borrows the histogram
+      CNB_STAT(if (tid == 0) { s_tmp[25] += (int)(clock64() - fq); })
     }
     if (tid == 0) clear_scalars();
     __syncthreads();
@@ -1185,6 +1235,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     for (int i = 0; i < 4; ++i) r_[i + 1] = *reinterpret_cast<const float4 *>(p + i * 128);
     r_[5] = (y0 + 4 < 128) ? *reinterpret_cast<const float4 *>(p + 4 * 128) : ninf;
     const uint32_t fbase = (uint32_t)c * (uint32_t)HW + (uint32_t)(y0 * 128 + lane * 4);
+    float lane_best = LOGITS ? NI : 0.0f;   // SW_HIST: best peak among this lane's 16 pixels
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       // threshold >= smallest positive float, so `b == max(.., thr)` also rejects b <= 0; it is
@@ -1194,6 +1245,18 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       const float v2 = fmax3(a.z, b.z, cc.z), v3 = fmax3(a.w, b.w, cc.w);
       const float l = __shfl_up_sync(0xffffffffu, v3, 1) + edge_l;
       const float r = __shfl_down_sync(0xffffffffu, v0, 1) + edge_r;
+      if (mode == SW_HIST) {
+        // bootstrap pass 1: no pushes, no divergence -- every lane just remembers its best peak (a logit peak is
+        // a heat peak: the sigmoid is monotone)
+        const float m01 = fmaxf(v0, v1), m23 = fmaxf(v2, v3);
+        const float floor_ = LOGITS ? NI : 0.0f;
+        const float c0 = (b.x == fmax3(l, m01, b.x)) ? b.x : floor_;
+        const float c1 = (b.y == fmax3(m01, v2, b.y)) ? b.y : floor_;
+        const float c2 = (b.z == fmax3(v1, m23, b.z)) ? b.z : floor_;
+        const float c3 = (b.w == fmax3(m23, r, b.w)) ? b.w : floor_;
+        lane_best = fmaxf(lane_best, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
+        continue;
+      }
       if (LOGITS) {
         // logit space: one compare per pixel against the logit image of the threshold; the (rare)
         // survivors are peak-tested exactly: b is a heat peak iff sigmoid(b) == sigmoid(3x3 max)
@@ -1222,14 +1285,25 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
         if (q3) push(b.w, f + 3, mode);
       }
     }
+    if (mode == SW_HIST) {
+      // one histogram entry per lane: the K-th largest of these <= 1024 lane maxima is a valid lower bound of the
+      // plane's K-th best peak (each is a distinct real peak), about the top 7 % of its ~1.8 k peaks
+      float v = LOGITS ? sigmoid_ref(lane_best) : lane_best;
+      if (pl.clamp_one) v = fminf(v, 1.0f);
+      if (v > 0.0f) atomicAdd(&fine[hist_bin(__float_as_uint(v))], 1);
+    }
   };
 
   int img = img_lo, c = (int)(p_begin - (long long)img * C);
   int stage = 0, par = 0;
   bool fresh = true;  // first unit of an image in this CTA (CTA-uniform)
+  CNB_STAT(long long st_t0 = clock64(); long long st_wait = 0; long long st_boot = 0; long long st_flush = 0;
+           int st_nboot = 0; int st_nflush = 0; long long st_q;)
   for (int u = 0; u < total_units; ++u) {
     const float *st = stages + (size_t)stage * (SEL_STAGE_BYTES / 4);
+    CNB_STAT(st_q = clock64();)
     mbar_wait(&full[stage], (uint32_t)par);
+    CNB_STAT(st_wait += clock64() - st_q; st_q = clock64();)
     if (*(volatile int *)&s_flag[u & 3]) compact(u & 3);   // set 3 units ago, before this plane's TMA was issued
     if (fresh) {
       // bootstrap (see header): histogram-only pass, K-th best of the plane, key pass
@@ -1246,6 +1320,7 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       __syncthreads();
       sweep(st, c, SW_KEYS);
       fresh = false;
+      CNB_STAT(st_boot += clock64() - st_q; ++st_nboot;)
     } else {
       sweep(st, c, SW_BOTH);
       if (warp == (u & (SEL_WARPS - 1))) refresh_thr();  // partial counts are valid too
@@ -1265,16 +1340,30 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
       }
     }
     // next unit
+    CNB_STAT(st_q = clock64();)
     if (++c == C) {
       flush(img);
       c = 0;
       ++img;
       fresh = true;
+      CNB_STAT(st_flush += clock64() - st_q; ++st_nflush;)
     } else if (u == total_units - 1) {
       flush(img);
+      CNB_STAT(st_flush += clock64() - st_q; ++st_nflush;)
     }
     if (++stage == SEL_STAGES) { stage = 0; par ^= 1; }
   }
+#ifdef CNB_SELECT_STATS
+  if (tid == 0) {
+    unsigned long long *d = g_select_stats[me];
+    d[0] = (unsigned long long)(clock64() - st_t0); d[1] = (unsigned long long)st_wait; d[2] = (unsigned long long)st_boot;
+    d[3] = (unsigned long long)st_flush; d[4] = (unsigned long long)s_tmp[25]; d[5] = (unsigned long long)total_units;
+    d[6] = (unsigned long long)st_nboot; d[7] = (unsigned long long)st_nflush; d[8] = (unsigned long long)s_tmp[24];
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    d[9] = smid;
+  }
+#endif
 }
 
 // ------------------------------------------------------------------ separate finalize kernel
@@ -1326,8 +1415,17 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
   // (any number of segments per image, so no grid shrinking).  An image boundary costs the crossing CTA a
   // flush + a bootstrap, about 2 planes' worth of cycles; only worth modelling when ranges are long.
   const bool hot_geom = nms && pl->use_tma && W == 128 && H == 128 && pl->rb == 128 && K <= 256;
+  // small batches: a one-plane segment per CTA means ~80 loose segments per image for the finalizing CTA to merge;
+  // three planes per CTA cost ~3 us more streaming and save more than that in the merge
+  if (hot_geom && C > 1 && pl->P < 3ll * n_cta) n_cta = (int)((pl->P + 2) / 3);
+  // An image boundary costs the crossing CTA a flush + a bootstrap (~12 k cycles), and -- being the slower one --
+  // it usually is the last to deliver the image that ENDS in it, i.e. it also runs that image's finalize
+  // (~10 k): 4 planes' worth of cycles balances best (swept 0..10 with tools/select_stats.py); long ranges only.
   int wb = 0;
-  if (hot_geom && C > 1 && pl->P / n_cta >= 8) wb = 2;
+  if (hot_geom && C > 1 && pl->P / n_cta >= 8) wb = 4;
+#ifdef CNB_SELECT_STATS
+  if (getenv("CNB_SELECT_WB") && hot_geom && C > 1 && pl->P / n_cta >= 8) wb = atoi(getenv("CNB_SELECT_WB"));
+#endif
   for (;;) {
     Part q;
     q.P = pl->P; q.n_cta = n_cta; q.C = C; q.wb = wb;
@@ -1337,11 +1435,17 @@ int make_select_plan(const float *src, int n_img, int C, int H, int W, int K, in
       wb = 0;
       continue;
     }
+    // segments an image can receive = CTAs whose range touches it; one sweep over the (monotone) ranges
     int ms = 1;
-    for (int b = 0; b < n_img; ++b) {
-      const int i0 = cta_of_plane((long long)b * C, q);
-      const int i1 = cta_of_plane((long long)(b + 1) * C - 1, q);
-      if (i1 - i0 + 1 > ms) ms = i1 - i0 + 1;
+    {
+      long long run_img = -1;
+      int run_len = 0;
+      for (int i = 0; i < n_cta; ++i) {
+        const long long lo = cta_first_plane(i, q) / C, hi = (cta_first_plane(i + 1, q) - 1) / C;
+        if (lo == run_img) ++run_len; else { run_img = lo; run_len = 1; }
+        if (run_len > ms) ms = run_len;
+        if (hi != lo) { run_img = hi; run_len = 1; }
+      }
     }
     if (hot_geom || (long long)ms * K <= SEL_FIN_MAX || n_cta == 1) {
       pl->max_slots = ms;
@@ -1443,5 +1547,11 @@ int run_select(const float *src, const SelectPlan &pl, const FinalizeOut &out, v
   return pl.nms ? launch_select<true>(src, pl, out, cand, cnt, done, thr, stream)
                 : launch_select<false>(src, pl, out, cand, cnt, done, thr, stream);
 }
+
+#ifdef CNB_SELECT_STATS
+extern "C" int cnb_debug_select_stats(unsigned long long *out, int n_cta) {
+  return cudaMemcpyFromSymbol(out, g_select_stats, sizeof(unsigned long long) * 10 * n_cta) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // namespace cnb
