@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bind-numa", action="store_true", help="pin the rank to its GPU's NUMA node before allocating")
     ap.add_argument("--no-secondary", action="store_true", help="skip the per-kernel secondary measurements (N=1 only)")
     args = ap.parse_args()
 
@@ -254,7 +255,10 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local)      # before any pinned allocation (first touch decides the node)
+    # Binding the rank to its GPU's NUMA node (before any pinned allocation) is OPT-IN: measured on this pool it
+    # cut the H2D rate of the chunked copy path from ~46-53 GB/s to 11-16 GB/s on several boxes (r2 runs), while
+    # the unbound process reaches the plain-copy rate.
+    numa = bind_to_gpu_numa_node(local) if args.bind_numa else "not bound (default; --bind-numa to bind)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

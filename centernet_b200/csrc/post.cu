@@ -322,3 +322,62 @@ int cnb_topk_keep(const float *rows, int b, int n_cap, int d, const int32_t *off
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ N4: detector input pre-processing
+// detectors/base_detector.py:37-65: cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of the uint8 HWC image,
+// (x / 255 - mean) / std in float64, HWC -> CHW fp32, optional mirrored copy (flip test) -- one pass, the image
+// crosses PCIe as uint8 (3 B / pixel instead of 12-24).  The warp restates OpenCV's fixed-point algorithm
+// (imgwarp.cpp): coordinates on a 1/1024 grid from the INVERTED matrix `minv` (cvRound = round half to even),
+// +16, >> 5 -> integer pixel + 5-bit phase; weights 32 * (32 - fy | fy) * (32 - fx | fx) (sum 32768);
+// value = (sum w * p + 2^14) >> 15 with out-of-image taps reading the border value 0.
+namespace cnb {
+__global__ void __launch_bounds__(256) k_preprocess(const unsigned char *__restrict__ img, int H, int W,
+                                                    const double *__restrict__ minv, const float *__restrict__ mean,
+                                                    const float *__restrict__ stdv, float *__restrict__ out, int oh,
+                                                    int ow, int flip) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= ow) return;
+  const double m0 = minv[0], m1 = minv[1], m2 = minv[2], m3 = minv[3], m4 = minv[4], m5 = minv[5];
+  const long long adelta = (long long)__double2ll_rn(__dmul_rn(__dmul_rn(m0, (double)x), 1024.0));
+  const long long bdelta = (long long)__double2ll_rn(__dmul_rn(__dmul_rn(m3, (double)x), 1024.0));
+  const long long X0 = (long long)__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16;
+  const long long Y0 = (long long)__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16;
+  auto sat_int = [](long long v) { return v > 2147483647ll ? 2147483647ll : (v < -2147483648ll ? -2147483648ll : v); };
+  const int X = (int)((sat_int(X0 - 16) + 16 + sat_int(adelta)) >> 5);   // saturate_cast<int> of each rounded term
+  const int Y = (int)((sat_int(Y0 - 16) + 16 + sat_int(bdelta)) >> 5);
+  int sx = X >> 5, sy = Y >> 5;
+  sx = min(max(sx, -32768), 32767);
+  sy = min(max(sy, -32768), 32767);
+  const int fx = X & 31, fy = Y & 31;
+  const int w0 = (32 - fy) * (32 - fx) * 32, w1 = (32 - fy) * fx * 32, w2 = fy * (32 - fx) * 32, w3 = fy * fx * 32;
+  const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
+  const bool x0ok = sx >= 0 && sx < W, x1ok = sx + 1 >= 0 && sx + 1 < W;
+  const size_t plane = (size_t)oh * ow;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int p00 = (y0ok && x0ok) ? img[((size_t)sy * W + sx) * 3 + c] : 0;
+    const int p01 = (y0ok && x1ok) ? img[((size_t)sy * W + sx + 1) * 3 + c] : 0;
+    const int p10 = (y1ok && x0ok) ? img[((size_t)(sy + 1) * W + sx) * 3 + c] : 0;
+    const int p11 = (y1ok && x1ok) ? img[((size_t)(sy + 1) * W + sx + 1) * 3 + c] : 0;
+    int v = (p00 * w0 + p01 * w1 + p10 * w2 + p11 * w3 + (1 << 14)) >> 15;
+    v = min(max(v, 0), 255);
+    const double r = __ddiv_rn(__dadd_rn(__ddiv_rn((double)v, 255.0), -(double)mean[c]), (double)stdv[c]);
+    const float f = (float)r;
+    out[c * plane + (size_t)y * ow + x] = f;
+    if (flip) out[(3 + c) * plane + (size_t)y * ow + (ow - 1 - x)] = f;
+  }
+}
+}  // namespace cnb
+
+extern "C" int cnb_preprocess_image(const uint8_t *image_hwc, int h, int w, const double *minv6, const float *mean3,
+                                    const float *std3, float *out, int out_h, int out_w, int flip_test, void *stream) {
+  CNB_REQUIRE(image_hwc && minv6 && mean3 && std3 && out, CNB_EINVAL, "cnb_preprocess_image: null pointer");
+  CNB_REQUIRE(h > 0 && w > 0 && out_h > 0 && out_w > 0 && h < 32768 && w < 32768, CNB_EINVAL,
+              "cnb_preprocess_image: bad shape");
+  dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)out_h);
+  cnb::k_preprocess<<<grid, 256, 0, (cudaStream_t)stream>>>(image_hwc, h, w, minv6, mean3, std3, out, out_h, out_w,
+                                                            flip_test ? 1 : 0);
+  CNB_CHECK_LAUNCH("cnb_preprocess_image");
+  cnb::count_launch();
+  return CNB_OK;
+}

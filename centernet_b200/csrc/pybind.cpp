@@ -177,6 +177,11 @@ PYBIND11_MODULE(_C, m) {
                         ptr<float>(thresh), ptr<void>(stream)),
           "cnb_topk_keep");
   });
+  m.def("preprocess_image", [](P img, int h, int w, P minv, P mean, P stdv, P out, int oh, int ow, int flip, P stream) {
+    check(cnb_preprocess_image(ptr<const uint8_t>(img), h, w, ptr<const double>(minv), ptr<const float>(mean),
+                               ptr<const float>(stdv), ptr<float>(out), oh, ow, flip, ptr<void>(stream)),
+          "cnb_preprocess_image");
+  });
   m.def("dcnv2_workspace_bytes", &cnb_dcnv2_workspace_bytes);
   m.def("dcnv2_forward", [](P input, P offset, P mask, P weight, P bias, P output, int b, int cin, int h, int w,
                             int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg, P ws,

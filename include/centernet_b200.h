@@ -306,6 +306,17 @@ int cnb_soft_nms(const float *rows, float *out, const int32_t *offsets, int n_im
 int cnb_topk_keep(const float *rows, int b, int n_cap, int d, const int32_t *offsets, int num_classes,
                   int max_per_image, uint8_t *keep, float *thresh, void *stream);
 
+/* ------------------------------------------- N4: detector input pre-processing
+ * detectors/base_detector.py:37-65 for one image: cv2.warpAffine(INTER_LINEAR,
+ * border 0) + (x/255 - mean)/std + HWC->CHW (+ mirrored copy when flip_test).
+ * image_hwc: uint8 [h,w,3] on the device; minv6: the INVERTED 2x3 float64 matrix
+ * (output pixel -> source coordinates, as cv::warpAffine derives it from its
+ * forward matrix); mean3/std3: fp32; out: [1 or 2, 3, out_h, out_w] fp32.
+ * Bit-identical to OpenCV's fixed-point bilinear warp. */
+int cnb_preprocess_image(const uint8_t *image_hwc, int h, int w, const double *minv6,
+                         const float *mean3, const float *std3, float *out,
+                         int out_h, int out_w, int flip_test, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

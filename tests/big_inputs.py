@@ -81,3 +81,18 @@ def exct_inputs(seed=319, B=1, C=80, H=128, W=128, n_obj=24):
             base[4, b, c, (y0 + y1) // 2, (x0 + x1) // 2] = sc[4]
     regs = [rng.random((B, 2, H, W), dtype=F32) for _ in range(4)]
     return [base[i] for i in range(5)], regs
+
+
+PRE_CASES = {   # name: (height, width, fix_res, flip_test, input_h, input_w)
+    "a": (375, 500, True, False, 512, 512), "b": (640, 427, True, True, 512, 512),
+    "c": (213, 317, False, False, 0, 0), "d": (480, 640, True, False, 384, 640),
+}
+
+
+def pre_image(name):
+    """Seeded uint8 BGR test image (smooth ramps + noise: every interpolation phase occurs), integer arithmetic only."""
+    h, w = PRE_CASES[name][:2]
+    rng = np.random.default_rng(1000 + ord(name))
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 3 + yy) % 256, (xx + yy * 2) % 256, (xx * yy // 7) % 256], 2)
+    return ((base * 3) // 5 + rng.integers(0, 100, (h, w, 3))).astype(np.uint8)
