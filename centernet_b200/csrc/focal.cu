@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(1024) k_reg_loss(const float *__restrict__ out
       const long long bm = i / D;
       const int b = (int)(bm / M);
       const long long sp = ind[bm];
+      if (sp < 0 || sp >= HW) continue;   // torch's gather raises on such an index; never read or write outside the map
       const float m = (mode == 3) ? mask_f[i] : (float)mask_u8[bm];
       float pred = output[((long long)b * D + d) * HW + sp];
       float tgt = target[i];

@@ -75,6 +75,11 @@ __global__ void __launch_bounds__(256) k_psroi_forward(const PsroiArgs a, long l
   const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (index >= count) return;
   const PsroiBin b = psroi_bin(a, index);
+  if (b.batch < 0 || b.batch >= a.B) {   // roi names an image that does not exist: empty bin instead of a wild read
+    out[index] = 0.f;
+    top_count[index] = 0.f;
+    return;
+  }
   const float *pl = a.data + ((long long)b.batch * a.C + b.c) * a.H * a.W;
   float sum = 0.f;
   int cnt = 0;
@@ -104,6 +109,7 @@ __global__ void __launch_bounds__(256) k_psroi_backward(const PsroiArgs a, long 
   if (index >= count) return;
   if (top_count[index] <= 0.f) return;
   const PsroiBin b = psroi_bin(a, index);
+  if (b.batch < 0 || b.batch >= a.B) return;
   const float dv = top_diff[index] / top_count[index];
   const long long plane = ((long long)b.batch * a.C + b.c) * a.H * a.W;
   const float *pl = a.data + plane;

@@ -322,45 +322,60 @@ __device__ void finalize_fill(const float *__restrict__ img, const SelectPlan &p
   G::sync();
 }
 
-// Write the K rows of image b from its sorted keys (raw top-K outputs and/or the fused ctdet epilogue).
+// Row k of image b from its key (raw top-K outputs and/or the fused ctdet epilogue, models/decode.py:472-493).
+// The four gathered values (reg x, reg y, wh w, wh h) may come pre-loaded (gath != nullptr).
+struct RowGather { float rx, ry, ww, wh_; };
+__device__ __forceinline__ RowGather gather_row(const SelectPlan &pl, int b, u64 key, const FinalizeOut &out) {
+  RowGather g = {0.5f, 0.5f, 0.f, 0.f};
+  if (!out.dets) return g;
+  const long long HW = (long long)pl.H * pl.W;
+  const uint32_t flat = key_idx(key);
+  const int cls = (int)(flat / (uint32_t)HW);
+  const int sp = (int)(flat - (uint32_t)cls * (uint32_t)HW);
+  if (out.reg) {  // decode.py:472-476
+    const float *r = out.reg + (size_t)b * 2 * HW;
+    g.rx = __ldg(r + sp);
+    g.ry = __ldg(r + HW + sp);
+  }
+  const int whc = out.cat_spec_wh ? 2 * pl.C : 2;  // :480-486
+  const float *wp = out.wh + ((size_t)b * whc + (out.cat_spec_wh ? 2 * cls : 0)) * HW;
+  g.ww = __ldg(wp + sp);
+  g.wh_ = __ldg(wp + HW + sp);
+  return g;
+}
+__device__ __forceinline__ void emit_one(const SelectPlan &pl, int b, int k, u64 key, const FinalizeOut &out,
+                                         const RowGather &g) {
+  const int K = pl.K;
+  const long long HW = (long long)pl.H * pl.W;
+  const float score = __uint_as_float(key_bits(key));
+  const uint32_t flat = key_idx(key);
+  const int cls = (int)(flat / (uint32_t)HW);
+  const int sp = (int)(flat - (uint32_t)cls * (uint32_t)HW);
+  const int yi = sp / pl.W, xi = sp - yi * pl.W;
+  const size_t o = (size_t)b * K + k;
+  if (out.scores) out.scores[o] = score;
+  if (out.inds) out.inds[o] = (int64_t)sp;
+  if (out.clses) out.clses[o] = cls;
+  if (out.ys) out.ys[o] = (float)yi;
+  if (out.xs) out.xs[o] = (float)xi;
+  if (out.dets) {
+    const float xs = (float)xi + g.rx, ys = (float)yi + g.ry;   // reg offsets, or +0.5 when there is no reg head (:477-479)
+    const float hw_ = g.ww * 0.5f, hh_ = g.wh_ * 0.5f;
+    float *d = out.dets + o * 6;  // :487-493
+    d[0] = xs - hw_;
+    d[1] = ys - hh_;
+    d[2] = xs + hw_;
+    d[3] = ys + hh_;
+    d[4] = score;
+    d[5] = (float)cls;
+  }
+}
+// Write the K rows of image b from its sorted keys.
 template <typename G>
 __device__ __forceinline__ void emit_rows(const SelectPlan &pl, int b, const u64 *sbuf, const FinalizeOut &out) {
-  const int tid = G::tid(), K = pl.K;
-  const long long HW = (long long)pl.H * pl.W;
-  for (int k = tid; k < K; k += G::n()) {
+  for (int k = G::tid(); k < pl.K; k += G::n()) {
     const u64 key = sbuf[k];
-    const float score = __uint_as_float(key_bits(key));
-    const uint32_t flat = key_idx(key);
-    const int cls = (int)(flat / (uint32_t)HW);
-    const int sp = (int)(flat - (uint32_t)cls * (uint32_t)HW);
-    const int yi = sp / pl.W, xi = sp - yi * pl.W;
-    const size_t o = (size_t)b * K + k;
-    if (out.scores) out.scores[o] = score;
-    if (out.inds) out.inds[o] = (int64_t)sp;
-    if (out.clses) out.clses[o] = cls;
-    if (out.ys) out.ys[o] = (float)yi;
-    if (out.xs) out.xs[o] = (float)xi;
-    if (out.dets) {
-      float xs = (float)xi, ys = (float)yi;
-      if (out.reg) {  // decode.py:472-476
-        const float *r = out.reg + (size_t)b * 2 * HW;
-        xs += __ldg(r + sp);
-        ys += __ldg(r + HW + sp);
-      } else {  // :477-479
-        xs += 0.5f;
-        ys += 0.5f;
-      }
-      const int whc = out.cat_spec_wh ? 2 * pl.C : 2;  // :480-486
-      const float *wp = out.wh + ((size_t)b * whc + (out.cat_spec_wh ? 2 * cls : 0)) * HW;
-      const float hw_ = __ldg(wp + sp) * 0.5f, hh_ = __ldg(wp + HW + sp) * 0.5f;
-      float *d = out.dets + o * 6;  // :487-493
-      d[0] = xs - hw_;
-      d[1] = ys - hh_;
-      d[2] = xs + hw_;
-      d[3] = ys + hh_;
-      d[4] = score;
-      d[5] = (float)cls;
-    }
+    emit_one(pl, b, k, key, out, gather_row(pl, b, key, out));
   }
 }
 
@@ -803,6 +818,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifdef CNB_SELECT_STATS
+// tuning build only (tools/select_stats.py rebuilds the library with -DCNB_SELECT_STATS): per CTA
+// [total, wait, bootstrap, flush, finalize] cycles and [units, bootstraps, flushes, finalizes] counts
+__device__ unsigned long long g_select_stats[SEL_MAX_CTA][10];
+#define CNB_STAT(x) x
+#else
+#define CNB_STAT(x)
+#endif
+
 enum { SW_BOTH = 0, SW_HIST = 1, SW_KEYS = 2 };  // what a qualifying pixel updates: histogram and/or key buffer
 
 // Finalize image b inside the hot kernel (all SEL_THREADS threads).  `local`: the keys are already in
@@ -815,6 +839,7 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
   const int tid = threadIdx.x, K = pl.K, cap = pl.seg_cap;
   int total;
   bool sorted = false;
+  CNB_STAT(long long ph[6]; ph[0] = clock64(); ph[1] = ph[2] = ph[3] = ph[4] = ph[5] = ph[0];)
   if (local) {
     total = n_local;
   } else {
@@ -888,6 +913,7 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
         }
       }
     };
+    CNB_STAT(ph[1] = clock64();)
     take(k0, tid);
     take(k1, tid + SEL_THREADS);
     for (int it0 = 2 * SEL_THREADS; it0 < items; it0 += 4 * SEL_THREADS) {   // small batches: many slots
@@ -924,6 +950,7 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
       sorted = true;
     }
   }
+  CNB_STAT(ph[2] = clock64();)
   const u64 *res = sbuf;
   if (!sorted && total > 256 && total <= SEL_CAP / 2) {
     // too many for the rank sort: one more cut, by a histogram of the keys already in shared memory (the K-th
@@ -956,15 +983,33 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
   }
   if (!sorted) {
     if (total <= 256) {
-      // few survivors: rank sort, 4 threads per key (every key counts the keys above it; keys are unique)
+      // few survivors: rank sort, 4 threads per key (every key counts the keys above it; keys are unique).  The
+      // key's owner issues its reg / wh gathers BEFORE counting -- they depend on the key, not on its rank -- so
+      // the L2 round trip runs under the sort, and the owner of a key ranked < K writes its row directly.
       u64 *dst = sbuf + SEL_CAP / 2;
       const int q = tid >> 2, part = tid & 3;
       const u64 mine = (q < total) ? sbuf[q] : 0ull;
-      int rank = 0;
-      if (q < total)
-        for (int t = part; t < total; t += 4) rank += (sbuf[t] > mine) ? 1 : 0;
+      RowGather rg = {0.5f, 0.5f, 0.f, 0.f};
+      if (q < total && part == 0 && total >= K) rg = gather_row(pl, b, mine, out);
+      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      if (q < total) {
+        int t = part;
+        for (; t + 12 < total; t += 16) {
+          r0 += (sbuf[t] > mine) ? 1 : 0;
+          r1 += (sbuf[t + 4] > mine) ? 1 : 0;
+          r2 += (sbuf[t + 8] > mine) ? 1 : 0;
+          r3 += (sbuf[t + 12] > mine) ? 1 : 0;
+        }
+        for (; t < total; t += 4) r0 += (sbuf[t] > mine) ? 1 : 0;
+      }
+      int rank = (r0 + r1) + (r2 + r3);
       rank += __shfl_xor_sync(0xffffffffu, rank, 1);
       rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+      if (total >= K) {
+        if (q < total && part == 0 && rank < K) emit_one(pl, b, rank, mine, out, rg);
+        __syncthreads();
+        return;
+      }
       for (int t = total + tid; t < max(total, K); t += SEL_THREADS) dst[t] = 0ull;
       if (q < total && part == 0) dst[rank] = mine;
       __syncthreads();
@@ -976,22 +1021,23 @@ __device__ void finalize_hot(const float *__restrict__ src, const SelectPlan &pl
       cta_sort_desc(sbuf, n);
     }
   }
+  CNB_STAT(ph[3] = clock64();)
   if (total < K) {
     const long long N = (long long)pl.C * pl.H * pl.W;
     finalize_fill<true, CtaGroup>(src + (long long)b * N, pl, const_cast<u64 *>(res), total, K, s_tmp, s_red);
   }
+  CNB_STAT(ph[4] = clock64();)
   emit_rows<CtaGroup>(pl, b, res, out);
   __syncthreads();
-}
-
 #ifdef CNB_SELECT_STATS
-// tuning build only (tools/select_stats.py rebuilds the library with -DCNB_SELECT_STATS): per CTA
-// [total, wait, bootstrap, flush, finalize] cycles and [units, bootstraps, flushes, finalizes] counts
-__device__ unsigned long long g_select_stats[SEL_MAX_CTA][10];
-#define CNB_STAT(x) x
-#else
-#define CNB_STAT(x)
+  if (tid == 0 && !local && b == 7) {
+    unsigned long long *d = g_select_stats[SEL_MAX_CTA - 1];
+    ph[5] = clock64();
+    d[0] = ph[1] - ph[0]; d[1] = ph[2] - ph[1]; d[2] = ph[3] - ph[2]; d[3] = ph[4] - ph[3]; d[4] = ph[5] - ph[4];
+    d[5] = (unsigned long long)total; d[6] = (unsigned long long)nslots;
+  }
 #endif
+}
 
 template <bool LOGITS>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
@@ -1122,8 +1168,17 @@ k_select_hot(const float *__restrict__ src, const SelectPlan pl, u64 *__restrict
     __syncthreads();
     if (fits) {
 #pragma unroll
-      for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j)
-        if (mine[j] != 0ull && key_bits(mine[j]) >= tb) buf[atomicAdd(&s_cnt[0], 1)] = mine[j];
+      for (int j = 0; j < SEL_CAP / SEL_THREADS; ++j) {   // warp-aggregated append: one shared atomic per warp
+        const bool ok = mine[j] != 0ull && key_bits(mine[j]) >= tb;
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        if (bal) {
+          const int leader = __ffs(bal) - 1;
+          int base_pos = 0;
+          if (lane == leader) base_pos = atomicAdd(&s_cnt[0], __popc(bal));
+          base_pos = __shfl_sync(0xffffffffu, base_pos, leader);
+          if (ok) buf[base_pos + __popc(bal & ((1u << lane) - 1u))] = mine[j];
+        }
+      }
     }
     __syncthreads();
     if (fits && s_cnt[0] > SEL_CAP / 2) {

@@ -169,7 +169,8 @@ int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_hea
  *   it is rebuilt on the fly from per-image object lists
  *   obj_cls[b,m] i32, obj_cx/obj_cy[b,m] i32 (ct_int), obj_radius[b,m] i32,
  *   obj_valid[b,m] u8 -- exactly the draw_umich_gaussian calls of
- *   datasets/sample/ctdet.py:111-117. */
+ *   datasets/sample/ctdet.py:111-117.  m <= 128 (the reference's max_objs,
+ *   datasets/dataset/coco.py:38); larger lists return CNB_EUNSUPPORTED. */
 size_t cnb_focal_workspace_bytes(long long n);
 int cnb_focal_loss(const float *pred, const float *gt, long long n, int logits,
                    float grad_scale, float *out2, float *grad,

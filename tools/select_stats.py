@@ -29,8 +29,10 @@ e1.record(); torch.cuda.synchronize()
 print("B=%d wb=%s: %.4f ms per call" % (B, os.environ.get("CNB_SELECT_WB", "default"), e0.elapsed_time(e1) / 60))
 lib = ctypes.CDLL(os.path.join(os.path.dirname(centernet_b200.__file__), "lib", "libcenternet_b200.so"))
 n = 148
-out = np.zeros((n, 10), np.uint64)
-assert lib.cnb_debug_select_stats(out.ctypes.data_as(ctypes.c_void_p), n) == 0
+full = np.zeros((192, 10), np.uint64)
+assert lib.cnb_debug_select_stats(full.ctypes.data_as(ctypes.c_void_p), 192) == 0
+out = full[:n]
+print("finalize phases of image 7 [loads+sync, take, cut+sort, fill, emit] cycles, survivors, segments:", [int(v) for v in full[191, :7]])
 o = out.astype(np.float64)
 names = ["total", "wait", "boot", "flush", "fin_cyc", "units", "n_boot", "n_flush", "n_fin", "smid"]
 print("mean", {k: round(float(o[:, i].mean()), 1) for i, k in enumerate(names)})
