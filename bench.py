@@ -32,7 +32,7 @@ UNIT = "images/s"
 B_PER_GPU, C, H, W, K = 64, 80, 128, 128, 100
 ALG_BYTES_PER_IMAGE = C * H * W * 4 + K * 4 * 4 + K * 6 * 4   # 5,246,880 B
 N_ROT = 3                                                      # rotating input batches (3 x 352 MB >> 126 MB L2)
-NCU_TRAFFIC_BYTES = 338720512 + 4057088                        # measured DRAM read + write of one launch (profiles/)
+NCU_TRAFFIC_BYTES = 341761536 + 3631360                        # measured DRAM read + write of one launch (profiles/r2)
 
 
 def workload_config(world):
@@ -335,6 +335,11 @@ def main():
     d2h = B_PER_GPU * K * 6 * 4
     e2e_value = None
     if args.e2e_steps > 0:
+        # one intra-op thread for the host side of this leg (what torchrun sets for every rank anyway): with the
+        # default of one thread per core the OpenMP team woken by the small host-side tensor ops spins on all
+        # cores and the chunked copy pipeline falls to half the link rate (measured r2: 25 vs 54 GB/s)
+        host_threads = torch.get_num_threads()
+        torch.set_num_threads(1)
         host = [tuple(x.cpu().pin_memory() for x in batches[i]) for i in range(2)]
         # what the link gives a plain pinned copy of the same buffers right now (shared hosts vary a lot)
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -367,6 +372,7 @@ def main():
         e2e_value = B_PER_GPU * world * args.e2e_steps / (float(t.item()) * 1e-3)
         h2d_gbs_per_rank = [round(h2d * args.e2e_steps / (m * 1e-3) / 1e9, 2) for m in e2e_rank_ms]
         del host
+        torch.set_num_threads(host_threads)
 
     secondary = {"ctdet_decode_from_logits": {"value": logit_value, "unit": UNIT,
                                               "note": "same workload, input = pre-sigmoid logits, sigmoid fused "
@@ -397,7 +403,7 @@ def main():
             "per_rank_ms_per_step": [round(m / args.steps, 5) for m in per_rank_ms],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
-                         "traffic_source": "profiles/r1_decode_hot_final_summary.csv (ncu --set full: "
+                         "traffic_source": "profiles/r2_select_hot_summary.csv (ncu --set full: "
                                            "dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                          "kernel": "k_select_hot (the whole decode call is this one launch)",
                          "alg_bytes_per_launch": ALG_BYTES_PER_IMAGE * B_PER_GPU},

@@ -369,6 +369,49 @@ __global__ void __launch_bounds__(256) k_preprocess(const unsigned char *__restr
 }
 }  // namespace cnb
 
+// cv2.resize(INTER_LINEAR) of a uint8 HWC image (base_detector.py:55 at test scales != 1): OpenCV's 11-bit
+// separable fixed point (resize.cpp) -- horizontal pass S = p0 * a0 + p1 * a1 with the source index clamped and
+// the phase zeroed at the borders, vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2 >> 2 with
+// only the row indices clamped; coefficients = cvRound(float phase * 2048).
+namespace cnb {
+__global__ void __launch_bounds__(256) k_resize_u8(const unsigned char *__restrict__ src, int H, int W,
+                                                   unsigned char *__restrict__ dst, int dh, int dw) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw) return;
+  const double sc_x = (double)W / (double)dw, sc_y = (double)H / (double)dh;
+  float fx = (float)__dadd_rn(__dmul_rn(__dadd_rn((double)x, 0.5), sc_x), -0.5);
+  int sx = (int)floorf(fx);
+  fx -= (float)sx;
+  if (sx < 0) { fx = 0.f; sx = 0; }
+  if (sx >= W - 1) { fx = 0.f; sx = W - 1; }
+  const int a0 = __float2int_rn(__fmul_rn(1.0f - fx, 2048.0f)), a1 = __float2int_rn(__fmul_rn(fx, 2048.0f));
+  const int sx1 = min(sx + 1, W - 1);
+  float fy = (float)__dadd_rn(__dmul_rn(__dadd_rn((double)y, 0.5), sc_y), -0.5);
+  const int sy = (int)floorf(fy);
+  fy -= (float)sy;
+  const int b0 = __float2int_rn(__fmul_rn(1.0f - fy, 2048.0f)), b1 = __float2int_rn(__fmul_rn(fy, 2048.0f));
+  const int r0 = min(max(sy, 0), H - 1), r1 = min(max(sy + 1, 0), H - 1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int s0 = src[((size_t)r0 * W + sx) * 3 + c] * a0 + src[((size_t)r0 * W + sx1) * 3 + c] * a1;
+    const int s1 = src[((size_t)r1 * W + sx) * 3 + c] * a0 + src[((size_t)r1 * W + sx1) * 3 + c] * a1;
+    int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    dst[((size_t)y * dw + x) * 3 + c] = (unsigned char)min(max(v, 0), 255);
+  }
+}
+}  // namespace cnb
+
+extern "C" int cnb_resize_image(const uint8_t *image_hwc, int h, int w, uint8_t *out_hwc, int out_h, int out_w,
+                                void *stream) {
+  CNB_REQUIRE(image_hwc && out_hwc, CNB_EINVAL, "cnb_resize_image: null pointer");
+  CNB_REQUIRE(h > 0 && w > 0 && out_h > 0 && out_w > 0 && h < 32768 && w < 32768, CNB_EINVAL, "cnb_resize_image: bad shape");
+  dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)out_h);
+  cnb::k_resize_u8<<<grid, 256, 0, (cudaStream_t)stream>>>(image_hwc, h, w, out_hwc, out_h, out_w);
+  CNB_CHECK_LAUNCH("cnb_resize_image");
+  cnb::count_launch();
+  return CNB_OK;
+}
+
 extern "C" int cnb_preprocess_image(const uint8_t *image_hwc, int h, int w, const double *minv6, const float *mean3,
                                     const float *std3, float *out, int out_h, int out_w, int flip_test, void *stream) {
   CNB_REQUIRE(image_hwc && minv6 && mean3 && std3 && out, CNB_EINVAL, "cnb_preprocess_image: null pointer");

@@ -177,6 +177,10 @@ PYBIND11_MODULE(_C, m) {
                         ptr<float>(thresh), ptr<void>(stream)),
           "cnb_topk_keep");
   });
+  m.def("resize_image", [](P img, int h, int w, P out, int oh, int ow, P stream) {
+    check(cnb_resize_image(ptr<const uint8_t>(img), h, w, ptr<uint8_t>(out), oh, ow, ptr<void>(stream)),
+          "cnb_resize_image");
+  });
   m.def("preprocess_image", [](P img, int h, int w, P minv, P mean, P stdv, P out, int oh, int ow, int flip, P stream) {
     check(cnb_preprocess_image(ptr<const uint8_t>(img), h, w, ptr<const double>(minv), ptr<const float>(mean),
                                ptr<const float>(stdv), ptr<float>(out), oh, ow, flip, ptr<void>(stream)),

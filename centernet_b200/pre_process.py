@@ -1,8 +1,8 @@
 """Mirror of BaseDetector.pre_process (src/lib/detectors/base_detector.py:37-65) on the device:
 the uint8 image crosses PCIe once (3 B/pixel instead of the 12-24 B/pixel of the normalised fp32 CHW batch the
 reference uploads), and the affine warp, the normalisation, the layout change and the flip-test copy are one
-kernel.  Bit-identical to the reference for `scale == 1` (the reference's cv2.resize to the same size is a copy);
-other test scales need cv2.resize's own fixed-point rule in front and are not implemented."""
+kernel.  At test scales != 1 the reference first runs cv2.resize (INTER_LINEAR); its fixed-point filter is a second
+small kernel (`cnb_resize_image`).  Bit-identical to the reference at every scale (tests/test_pre.py)."""
 import numpy as np
 import torch
 
@@ -50,8 +50,6 @@ def pre_process(image, scale, mean, std, fix_res=True, input_h=512, input_w=512,
                 flip_test=False, device=None):
     """image: uint8 [H, W, 3] numpy array (BGR, as cv2.imread) or CUDA uint8 tensor.  Returns (images, meta) like
     the reference: images fp32 CUDA tensor [1 or 2, 3, inp_h, inp_w]; meta = {'c', 's', 'out_height', 'out_width'}."""
-    if scale != 1:
-        raise NotImplementedError("pre_process: only the test-time default scale 1 is implemented on the device")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if isinstance(image, torch.Tensor):
         if not image.is_cuda or image.dtype != torch.uint8:
@@ -62,6 +60,10 @@ def pre_process(image, scale, mean, std, fix_res=True, input_h=512, input_w=512,
         img = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(dev, non_blocking=True)
     height, width = int(img.shape[0]), int(img.shape[1])
     new_height, new_width = int(height * scale), int(width * scale)
+    if (new_height, new_width) != (height, width):         # cv2.resize(image, (new_width, new_height)), :55
+        resized = torch.empty((new_height, new_width, 3), dtype=torch.uint8, device=dev)
+        C.resize_image(ptr(img), height, width, ptr(resized), new_height, new_width, stream_ptr(resized))
+        img = resized
     if fix_res:
         inp_height, inp_width = input_h, input_w
         c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
@@ -75,7 +77,7 @@ def pre_process(image, scale, mean, std, fix_res=True, input_h=512, input_w=512,
     mean_t = torch.tensor(np.asarray(mean, np.float32).reshape(3), device=dev)
     std_t = torch.tensor(np.asarray(std, np.float32).reshape(3), device=dev)
     out = torch.empty((2 if flip_test else 1, 3, inp_height, inp_width), dtype=torch.float32, device=dev)
-    C.preprocess_image(ptr(img), height, width, ptr(minv), ptr(mean_t), ptr(std_t), ptr(out), inp_height, inp_width,
+    C.preprocess_image(ptr(img), new_height, new_width, ptr(minv), ptr(mean_t), ptr(std_t), ptr(out), inp_height, inp_width,
                        int(bool(flip_test)), stream_ptr(out))
     meta = {'c': c, 's': s, 'out_height': inp_height // down_ratio, 'out_width': inp_width // down_ratio}
     return out, meta

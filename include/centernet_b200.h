@@ -314,6 +314,10 @@ int cnb_topk_keep(const float *rows, int b, int n_cap, int d, const int32_t *off
  * (output pixel -> source coordinates, as cv::warpAffine derives it from its
  * forward matrix); mean3/std3: fp32; out: [1 or 2, 3, out_h, out_w] fp32.
  * Bit-identical to OpenCV's fixed-point bilinear warp. */
+/* cv2.resize(image, (out_w, out_h)) with INTER_LINEAR for uint8 [h,w,3] images (the multi-scale test path of
+ * base_detector.py:55), bit-identical to OpenCV's fixed-point filter. */
+int cnb_resize_image(const uint8_t *image_hwc, int h, int w, uint8_t *out_hwc, int out_h, int out_w,
+                     void *stream);
 int cnb_preprocess_image(const uint8_t *image_hwc, int h, int w, const double *minv6,
                          const float *mean3, const float *std3, float *out,
                          int out_h, int out_w, int flip_test, void *stream);

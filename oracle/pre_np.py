@@ -69,9 +69,36 @@ def warp_affine_linear(img, m_fwd, dsize):
     return np.clip((out + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
 
 
+def resize_linear_u8(img, dsize):
+    """cv2.resize(img, dsize) (INTER_LINEAR) for uint8 images: OpenCV's 11-bit fixed-point separable filter
+    (resize.cpp: coefficients saturate_cast<short>(w * 2048) from a float32 phase; horizontally the source index is
+    clamped and the phase zeroed at the borders, vertically only the row indices are clamped; vertical pass
+    ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2 >> 2)."""
+    img = np.asarray(img, np.uint8)
+    H, W = img.shape[:2]
+    dw, dh = dsize
+    d = np.arange(dw)
+    f = ((d + 0.5) * (W / dw) - 0.5).astype(F32)
+    sx = np.floor(f).astype(np.int64)
+    f = (f - sx).astype(F32)
+    lo = sx < 0; f[lo] = 0; sx[lo] = 0
+    hi = sx >= W - 1; f[hi] = 0; sx[hi] = W - 1
+    ax0 = np.rint((F32(1) - f) * F32(2048)).astype(np.int64); ax1 = np.rint(f * F32(2048)).astype(np.int64)
+    sx1 = np.minimum(sx + 1, W - 1)
+    d = np.arange(dh)
+    f = ((d + 0.5) * (H / dh) - 0.5).astype(F32)
+    sy = np.floor(f).astype(np.int64)
+    f = (f - sy).astype(F32)
+    by0 = np.rint((F32(1) - f) * F32(2048)).astype(np.int64); by1 = np.rint(f * F32(2048)).astype(np.int64)
+    r0 = np.clip(sy, 0, H - 1); r1 = np.clip(sy + 1, 0, H - 1)
+    src = img.astype(np.int64)
+    hrow = src[:, sx] * ax0[None, :, None] + src[:, sx1] * ax1[None, :, None]
+    out = (((by0[:, None, None] * (hrow[r0] >> 4)) >> 16) + ((by1[:, None, None] * (hrow[r1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def pre_process(image, scale, mean, std, fix_res=True, input_h=512, input_w=512, pad=31, down_ratio=4, flip_test=False):
-    """detectors/base_detector.py:37-65 for scale == 1 (cv2.resize to the same size is a copy)."""
-    assert scale == 1, "the oracle restates the test-time default (scale 1); other scales need cv2.resize's fixed point"
+    """detectors/base_detector.py:37-65."""
     height, width = image.shape[0:2]
     new_height, new_width = int(height * scale), int(width * scale)
     if fix_res:
@@ -84,7 +111,8 @@ def pre_process(image, scale, mean, std, fix_res=True, input_h=512, input_w=512,
         c = np.array([new_width // 2, new_height // 2], dtype=F32)
         s = np.array([inp_width, inp_height], dtype=F32)
     trans_input = forward_affine(c, s, [inp_width, inp_height])
-    inp = warp_affine_linear(image, trans_input, (inp_width, inp_height))
+    resized = resize_linear_u8(image, (new_width, new_height))          # identity when scale == 1
+    inp = warp_affine_linear(resized, trans_input, (inp_width, inp_height))
     mean = np.asarray(mean, F32).reshape(1, 1, 3); std = np.asarray(std, F32).reshape(1, 1, 3)
     inp = ((inp / 255. - mean) / std).astype(F32)
     images = inp.transpose(2, 0, 1).reshape(1, 3, inp_height, inp_width)

@@ -83,9 +83,11 @@ def exct_inputs(seed=319, B=1, C=80, H=128, W=128, n_obj=24):
     return [base[i] for i in range(5)], regs
 
 
-PRE_CASES = {   # name: (height, width, fix_res, flip_test, input_h, input_w)
-    "a": (375, 500, True, False, 512, 512), "b": (640, 427, True, True, 512, 512),
-    "c": (213, 317, False, False, 0, 0), "d": (480, 640, True, False, 384, 640),
+PRE_CASES = {   # name: (height, width, fix_res, flip_test, input_h, input_w, test scale)
+    "a": (375, 500, True, False, 512, 512, 1), "b": (640, 427, True, True, 512, 512, 1),
+    "c": (213, 317, False, False, 0, 0, 1), "d": (480, 640, True, False, 384, 640, 1),
+    "e": (375, 500, True, False, 512, 512, 0.5), "f": (213, 317, False, True, 0, 0, 1.5),
+    "g": (300, 400, True, False, 512, 512, 1.25),
 }
 
 

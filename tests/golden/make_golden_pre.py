@@ -23,13 +23,13 @@ class Opt(object):
     pass
 
 
-def run(image, fix_res, flip, input_h=512, input_w=512):
+def run(image, fix_res, flip, input_h=512, input_w=512, scale=1):
     d = types.SimpleNamespace()
     d.opt = Opt(); d.opt.fix_res = fix_res; d.opt.input_h = input_h; d.opt.input_w = input_w; d.opt.pad = 31
     d.opt.flip_test = flip; d.opt.down_ratio = 4
     d.mean = np.array([0.408, 0.447, 0.470], np.float32).reshape(1, 1, 3)
     d.std = np.array([0.289, 0.274, 0.278], np.float32).reshape(1, 1, 3)
-    images, meta = BaseDetector.pre_process(d, image, 1)
+    images, meta = BaseDetector.pre_process(d, image, scale)
     return images.numpy(), meta
 
 
@@ -38,9 +38,9 @@ def main():
     sys.path.insert(0, os.path.dirname(HERE))
     import big_inputs as BI
     out = {}
-    for name, (h, w, fix, flip, ih, iw) in BI.PRE_CASES.items():
+    for name, (h, w, fix, flip, ih, iw, sc) in BI.PRE_CASES.items():
         img = BI.pre_image(name)
-        images, meta = run(img, fix, flip, ih or 512, iw or 512)
+        images, meta = run(img, fix, flip, ih or 512, iw or 512, sc)
         # inputs are rebuilt by tests/big_inputs.py; of the output (3-6 MB of float32 per case) the CRC and a
         # strided sample are stored
         out["img_crc_" + name] = np.uint32(zlib.crc32(np.ascontiguousarray(img).view(np.uint8)))

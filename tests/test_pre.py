@@ -27,10 +27,10 @@ def _check(name, images, meta, g):
 @pytest.mark.parametrize("name", sorted(BI.PRE_CASES))
 def test_oracle_pre_process(name):
     g = golden("pre")
-    h, w, fix, flip, ih, iw = BI.PRE_CASES[name]
+    h, w, fix, flip, ih, iw, sc = BI.PRE_CASES[name]
     img = BI.pre_image(name)
     assert np.uint32(zlib.crc32(img.view(np.uint8))) == g["img_crc_" + name]
-    images, meta = pre_np.pre_process(img, 1, MEAN, STD, fix_res=fix, input_h=ih or 512, input_w=iw or 512, flip_test=flip)
+    images, meta = pre_np.pre_process(img, sc, MEAN, STD, fix_res=fix, input_h=ih or 512, input_w=iw or 512, flip_test=flip)
     _check(name, images, meta, g)
 
 
@@ -38,6 +38,8 @@ def test_oracle_warp_matches_cv2_when_present():
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(3)
     img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    for dsize in ((65, 48), (131, 97), (200, 150), (262, 194), (17, 301)):
+        np.testing.assert_array_equal(pre_np.resize_linear_u8(img, dsize), cv2.resize(img, dsize))
     for c, s, out in (((65.5, 48.5), 131.0, (160, 128)), ((40.0, 60.0), (200.0, 90.0), (96, 64)), ((65.0, 48.0), 64.0, (256, 256))):
         m = pre_np.forward_affine(np.array(c, np.float32), s, out)
         np.testing.assert_array_equal(pre_np.warp_affine_linear(img, m, out), cv2.warpAffine(img, m, out, flags=cv2.INTER_LINEAR))
@@ -48,9 +50,7 @@ def test_oracle_warp_matches_cv2_when_present():
 def test_gpu_pre_process(name):
     from centernet_b200 import pre_process as P
     g = golden("pre")
-    h, w, fix, flip, ih, iw = BI.PRE_CASES[name]
-    images, meta = P.pre_process(BI.pre_image(name), 1, MEAN, STD, fix_res=fix, input_h=ih or 512, input_w=iw or 512,
+    h, w, fix, flip, ih, iw, sc = BI.PRE_CASES[name]
+    images, meta = P.pre_process(BI.pre_image(name), sc, MEAN, STD, fix_res=fix, input_h=ih or 512, input_w=iw or 512,
                                  flip_test=flip)
     _check(name, images.cpu().numpy(), meta, g)
-    with pytest.raises(NotImplementedError):
-        P.pre_process(BI.pre_image(name), 0.5, MEAN, STD)
