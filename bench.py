@@ -238,7 +238,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bind-numa", action="store_true", help="pin the rank to its GPU's NUMA node before allocating")
+    ap.add_argument("--bind-numa", dest="bind_numa", action="store_true", default=None,
+                    help="pin the rank to its GPU's NUMA node before allocating (default: only when world > 1)")
+    ap.add_argument("--no-bind-numa", dest="bind_numa", action="store_false")
     ap.add_argument("--no-secondary", action="store_true", help="skip the per-kernel secondary measurements (N=1 only)")
     args = ap.parse_args()
 
@@ -255,10 +257,12 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # Binding the rank to its GPU's NUMA node (before any pinned allocation) is OPT-IN: measured on this pool it
-    # cut the H2D rate of the chunked copy path from ~46-53 GB/s to 11-16 GB/s on several boxes (r2 runs), while
-    # the unbound process reaches the plain-copy rate.
-    numa = bind_to_gpu_numa_node(local) if args.bind_numa else "not bound (default; --bind-numa to bind)"
+    # Host placement of the e2e leg.  (Earlier r2 runs that bound a single rank measured 11-16 GB/s: that was the
+    # OpenMP team of the host process spinning on the 64 bound cores, fixed since by the single intra-op thread.)
+    # N > 1: every rank keeps its pinned staging buffers on its own GPU's NUMA node (the 8-rank runs measured 43-53 GB/s
+    # per rank unbound, run to run, and 52.3 GB/s bound); N = 1: the default placement measured fastest
+    bind = args.bind_numa if args.bind_numa is not None else world > 1
+    numa = bind_to_gpu_numa_node(local) if bind else "not bound (--bind-numa to bind)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

@@ -499,6 +499,14 @@ int dcn_forward_tc_prepared(const float *input, int input_nhwc, const float *off
 int dcn_forward_tc(const float *input, const float *offset, const float *mask, const float *weight,
                    const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
                    int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream);
+size_t dcn_tc_bwd_workspace_bytes(int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int ph, int dh, int dg);
+int dcn_backward_data_tc(const float *input, const float *offset, const float *mask, const float *weight,
+                         const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask, int b,
+                         int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                         int dg, void *workspace, cudaStream_t stream, int xt_ready);
+int dcn_backward_weight_tc(const float *input, const float *offset, const float *mask, const float *grad_output,
+                           float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw,
+                           int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream, int xt_ready);
 }
 
 using namespace cnb;
@@ -514,6 +522,14 @@ size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh,
       stride <= 0 || dil <= 0 || pad < 0)
     return 0;
   return dcn_tc_workspace_bytes(b, cin, h, w, cout, kh, kw, stride, pad, dil, dg);
+}
+
+size_t cnb_dcnv2_backward_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw, int stride, int pad,
+                                          int dil, int dg) {
+  if (b <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || dg <= 0 || cin % dg != 0 || kh * kw > DCN_KT_MAX ||
+      stride <= 0 || dil <= 0 || pad < 0)
+    return 0;
+  return dcn_tc_bwd_workspace_bytes(b, cin, h, w, cout, kh, kw, stride, pad, dil, dg);
 }
 
 size_t cnb_dcnv2_wtiles_bytes(int cin, int cout, int kh, int kw, int dg) {
@@ -630,7 +646,7 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
                        const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask,
                        float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw,
                        int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_groups,
-                       void *, size_t, void *stream_) {
+                       void *workspace, size_t workspace_bytes, void *stream_) {
   CNB_REQUIRE(input && offset && mask && weight && grad_output, CNB_EINVAL, "cnb_dcnv2_backward: null pointer");
   DcnShape s;
   int rc = check_shape("cnb_dcnv2_backward", b, cin, h, w, cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h,
@@ -641,7 +657,18 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
   const int tiles = (int)((HWo + DCN_TP - 1) / DCN_TP);
   constexpr int KC = DCN_CK * DCN_KT_MAX;
   int launches = 0;
-  if (grad_input || grad_offset || grad_mask) {
+  // tensor-core path (dcnv2_bwd_tc.cu) when the caller provides the workspace; else the fp32 CUDA-core kernels below
+  const bool iso = stride_h == stride_w && pad_h == pad_w && dil_h == dil_w;
+  const size_t need = (iso && kh * kw <= DCN_KT_MAX)
+                          ? dcn_tc_bwd_workspace_bytes(b, cin, h, w, cout, kh, kw, stride_h, pad_h, dil_h, deformable_groups)
+                          : 0;
+  const bool tc = workspace && need > 0 && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0;
+  if (tc && (grad_input || grad_offset || grad_mask)) {
+    rc = dcn_backward_data_tc(input, offset, mask, weight, grad_output, grad_input, grad_offset, grad_mask, b, cin, h, w,
+                              cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups, workspace,
+                              stream, 0);
+    if (rc != CNB_OK) return rc;
+  } else if (grad_input || grad_offset || grad_mask) {
     const size_t smem = sizeof(BwdMeta) * DCN_KT_MAX * DCN_TP + sizeof(float) * KC * DCN_TP +
                         sizeof(float) * 64 * DCN_TP + sizeof(float) * 64 * (KC + 1) +
                         3 * sizeof(float) * DCN_KT_MAX * DCN_TP;
@@ -657,7 +684,13 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward data");
     ++launches;
   }
-  if (grad_weight) {
+  if (tc && grad_weight && cout <= 256) {
+    rc = dcn_backward_weight_tc(input, offset, mask, grad_output, grad_weight, grad_bias, b, cin, h, w, cout, kh, kw, stride_h,
+                                stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups, workspace, stream,
+                                (grad_input || grad_offset || grad_mask) ? 1 : 0);
+    if (rc != CNB_OK) return rc;
+    grad_bias = nullptr;   // done by the weight pass
+  } else if (grad_weight) {
     const int cpg = cin / deformable_groups;
     const int chunks = deformable_groups * ((cpg + DCN_CK - 1) / DCN_CK);
     const int cot = (cout + 63) / 64;

@@ -1,0 +1,839 @@
+// DCNv2 backward with both dense contractions on the 5th-generation tensor cores (tcgen05 / UMMA, 3xTF32).
+// Reference: dcn_v2_cuda.c:104-241 (per sample: SGEMM columns = W^T . dY, col2im_coord, col2im, im2col again,
+// SGEMM dW += dY . columns^T, SGEMV dBias) and dcn_v2_im2col_cuda.cu:182-312.
+//
+// The column gradient
+//     dcol[b][p][q = (channel block, tap)][32 ch] = sum_o dY[b][o][p] * W[o][ch][tap]
+// is a plain GEMM (M = pixels, N = Cin*9, K = Cout).  k_dcn_bwd_dcol_tc runs it as a persistent TMA -> UMMA ->
+// TMEM pipeline (both operands arrive pre-split into TF32 hi/lo tiles; no thread touches an operand) and writes
+// dcol channels-last, so that everything after it moves whole 128-byte lines:
+//   k_dcn_bwd_offmask   one (tap, 4 pixels) per warp, lane = (pixel, 4-channel quad): reads the dcol line and the
+//                       four bilinear corner lines of the channels-last input, reduces dMask / dOffset over the
+//                       channels in a fixed order (deterministic; dcn_v2_im2col_cuda.cu:241-312) and scatters
+//                       dX = dcol * mask * corner weight with 16-byte vector reductions (red.global.add.v4.f32:
+//                       a quarter of the reference's per-element atomicAdds, :182-239) into a channels-last dX
+//   k_dcn_bwd_dx_nchw   adds the channels-last dX into the caller's NCHW gradient
+// The weight gradient dW[o][ch][tap] = sum_{b,p} dY[b][o][p] * col[b][p][ch][tap] is a GEMM with K = pixels:
+// k_dcn_bwd_weight_tc rebuilds the masked column tile in shared memory exactly as the forward sampler does
+// (never in HBM), keeps a [128 rows = 4 chunks x 32 ch] x Cout accumulator in TMEM over its whole pixel range and
+// writes one partial per CTA; k_dcn_bwd_wreduce adds the partials in a fixed order (deterministic).
+#include "dcnv2_tc.cuh"
+
+namespace cnb {
+
+constexpr int BW_STAGES = 3;
+constexpr int BW_STAGE_BYTES = 4 * TC_A_BYTES;     // A hi, A lo, B hi, B lo: 4 x (128 rows x 32 k x 4 B) = 64 KB
+constexpr int BW_TILE_FLOATS = 2 * TC_TP * TC_K;   // one operand tile, hi + lo
+constexpr int BW_THREADS = 192;                    // warps 0-3 epilogue, 4 MMA, 5 TMA
+
+struct BwdGeom {
+  int KS;      // 32-wide slices of Cout (K of the dcol GEMM)
+  int Q;       // chunks (channel block, tap) = nb * 9
+  int RG;      // groups of 4 chunks = 128 UMMA rows
+  int Qp;      // RG * 4: chunk pitch of dcol
+  int tiles;   // pixel tiles per image
+};
+static BwdGeom bwd_geom(const DcnShapeTc &s) {
+  BwdGeom g;
+  g.KS = (s.Cout + TC_K - 1) / TC_K;
+  g.Q = s.nb * TC_NT;
+  g.RG = (g.Q + 3) / 4;
+  g.Qp = g.RG * 4;
+  g.tiles = s.tiles_x * s.tiles_y;
+  return g;
+}
+
+// W[Cout][Cin][KT] -> per (row group rg, slice ks): [128 rows = (chunk ql, ch)][32 k = output channel], hi then lo
+__global__ void __launch_bounds__(256) k_bwd_prep_w(const float *__restrict__ w, const DcnShapeTc s, const BwdGeom g,
+                                                    float *__restrict__ wtt) {
+  const int KT = s.kh * s.kw, cpg = s.Cin / s.dg;
+  const int rg = blockIdx.x / g.KS, ks = blockIdx.x - rg * g.KS;
+  unsigned char *hi = reinterpret_cast<unsigned char *>(wtt + (size_t)blockIdx.x * BW_TILE_FLOATS);
+  unsigned char *lo = hi + TC_A_BYTES;
+  for (int i = threadIdx.x; i < TC_TP * TC_K; i += blockDim.x) {
+    const int k = i & (TC_K - 1), row = i >> 5;
+    const int q = rg * 4 + (row >> 5), ch = row & 31;
+    const int bi = q / TC_NT, tap = q - bi * TC_NT;
+    const int gi = bi / s.cbs_pg, cw = (bi - gi * s.cbs_pg) * TC_CB + ch;
+    const int o = ks * TC_K + k;
+    float v = 0.f;
+    if (q < g.Q && o < s.Cout && cw < cpg && tap < KT) v = __ldg(w + ((size_t)o * s.Cin + gi * cpg + cw) * KT + tap);
+    const float h = tf32_hi(v);
+    *reinterpret_cast<float *>(hi + tc_tile_off(row, k)) = h;
+    *reinterpret_cast<float *>(lo + tc_tile_off(row, k)) = v - h;
+  }
+}
+
+// dY [B][Cout][HWo] -> per (image, pixel tile, slice ks): [128 px][32 k = output channel], hi then lo.  grid (tiles, KS, B)
+__global__ void __launch_bounds__(256) k_bwd_prep_gy(const float *__restrict__ gy, const DcnShapeTc s, const BwdGeom g,
+                                                     float *__restrict__ gyt) {
+  const int t = blockIdx.x, ks = blockIdx.y, b = blockIdx.z;
+  const int pp = threadIdx.x & (TC_TP - 1), half = threadIdx.x >> 7;
+  const int ho = (t / s.tiles_x) * s.th + pp / s.tw, wo = (t % s.tiles_x) * s.tw + pp % s.tw;
+  const bool ok = ho < s.Ho && wo < s.Wo;
+  const long long HWo = (long long)s.Ho * s.Wo, p = (long long)ho * s.Wo + wo;
+  unsigned char *hi = reinterpret_cast<unsigned char *>(gyt + ((size_t)((size_t)b * g.tiles + t) * g.KS + ks) * BW_TILE_FLOATS);
+  unsigned char *lo = hi + TC_A_BYTES;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    const int kq = half * 4 + kc;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = ks * TC_K + kq * 4 + j;
+      v[j] = (ok && o < s.Cout) ? __ldg(gy + ((long long)b * s.Cout + o) * HWo + p) : 0.f;
+    }
+    const float4 h4 = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
+    const uint32_t off = tc_tile_off(pp, kq * 4);
+    *reinterpret_cast<float4 *>(hi + off) = h4;
+    *reinterpret_cast<float4 *>(lo + off) = make_float4(v[0] - h4.x, v[1] - h4.y, v[2] - h4.z, v[3] - h4.w);
+  }
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc),
+               "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+      "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ dcol = dY^T . W   (item = image, pixel tile, row group)
+__global__ void __launch_bounds__(BW_THREADS, 1)
+k_dcn_bwd_dcol_tc(const float *__restrict__ gyt, const float *__restrict__ wtt, float *__restrict__ dcol,
+                  const DcnShapeTc s, const BwdGeom g, const int n_items) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ __align__(8) uint64_t full[BW_STAGES], empty[BW_STAGES], tm_full[2], tm_empty[2];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TC_EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == TC_WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+
+  if (warp == TC_WARP_TMA) {
+    if (lane == 0) {
+      int stage = 0, ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rg = item % g.RG, bt = item / g.RG;          // bt = image * tiles + tile
+        for (int ks = 0; ks < g.KS; ++ks) {
+          mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
+          unsigned char *dst = tc_smem + (size_t)stage * BW_STAGE_BYTES;
+          const unsigned char *a = reinterpret_cast<const unsigned char *>(gyt + ((size_t)bt * g.KS + ks) * BW_TILE_FLOATS);
+          const unsigned char *bsrc = reinterpret_cast<const unsigned char *>(wtt + ((size_t)rg * g.KS + ks) * BW_TILE_FLOATS);
+          mbar_expect_tx(&full[stage], (uint32_t)BW_STAGE_BYTES);
+          for (uint32_t off = 0; off < 2u * TC_A_BYTES; off += 8192u) bulk_g2s(dst + off, a + off, 8192u, &full[stage]);
+          for (uint32_t off = 0; off < 2u * TC_A_BYTES; off += 8192u)
+            bulk_g2s(dst + 2 * TC_A_BYTES + off, bsrc + off, 8192u, &full[stage]);
+          if (++stage == BW_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == TC_WARP_MMA) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
+      int stage = 0, ph = 0, acc = 0, aph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(&tm_empty[acc], (uint32_t)(aph ^ 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tm + (uint32_t)(acc * 128);
+        for (int ks = 0; ks < g.KS; ++ks) {
+          mbar_wait(&full[stage], (uint32_t)ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ah = smem_u32(tc_smem + (size_t)stage * BW_STAGE_BYTES), al = ah + TC_A_BYTES;
+          const uint32_t bh = al + TC_A_BYTES, bl = bh + TC_A_BYTES;
+#pragma unroll
+          for (int k8 = 0; k8 < TC_K / 8; ++k8) {
+            const uint32_t koff = (uint32_t)k8 * 2u * TC_LBO;
+            const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
+            const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
+            umma_tf32(d_tmem, dal, dbh, idesc, (ks > 0 || k8 > 0) ? 1u : 0u);   // lo * hi  (small terms first)
+            umma_tf32(d_tmem, dah, dbl, idesc, 1u);                             // hi * lo
+            umma_tf32(d_tmem, dah, dbh, idesc, 1u);                             // hi * hi
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == BW_STAGES) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(&tm_full[acc]);
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // epilogue: TMEM lane = pixel, 32 columns = the 32 channels of one chunk -> one 128-byte line of dcol
+    const int qw = warp;
+    const long long HWo = (long long)s.Ho * s.Wo;
+    int acc = 0, aph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rg = item % g.RG, bt = item / g.RG;
+      const int t = bt % g.tiles, b = bt / g.tiles;
+      const int pp = qw * 32 + lane;
+      const int ho = (t / s.tiles_x) * s.th + pp / s.tw, wo = (t % s.tiles_x) * s.tw + pp % s.tw;
+      const bool ok = ho < s.Ho && wo < s.Wo;
+      float *dst = dcol + (((long long)b * HWo + (long long)ho * s.Wo + wo) * g.Qp + rg * 4) * TC_CB;
+      mbar_wait(&tm_full[acc], (uint32_t)aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tm + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * 128);
+#pragma unroll 1
+      for (int ql = 0; ql < 4; ++ql) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(ql * 32), v);
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4 *>(dst + ql * TC_CB)[j] =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_tc(&tm_empty[acc]);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == TC_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(256));
+}
+
+// ------------------------------------------------------------------ dMask / dOffset (+ the dX scatter)
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+// Geometry of one (tap, pixel): fractional parts, mask and (hl*W + wl + W + 1) << 6 | flags
+// (bit 0-3: corner in range, 4: sampling point inside (-1,H)x(-1,W), 5: pixel inside the output map).
+struct __align__(16) BwdMetaTc {
+  float lh, lw, m;
+  int packed;
+};
+__device__ __forceinline__ BwdMetaTc bwd_meta(const DcnShapeTc &s, const float *__restrict__ off_img,
+                                              const float *__restrict__ mask_img, int gi, int tap, int ho, int wo) {
+  const int KT = s.kh * s.kw;
+  const long long HWo = (long long)s.Ho * s.Wo;
+  BwdMetaTc mt;
+  mt.lh = mt.lw = mt.m = 0.f;
+  mt.packed = 0;
+  if (ho < s.Ho && wo < s.Wo && tap < KT) {
+    const long long p = (long long)ho * s.Wo + wo;
+    const int ki = tap / s.kw, kj = tap - ki * s.kw;
+    const float *op = off_img + ((long long)gi * 2 * KT + 2 * tap) * HWo + p;
+    const float dy = __ldg(op), dx = __ldg(op + HWo);
+    mt.m = __ldg(mask_img + ((long long)gi * KT + tap) * HWo + p);
+    const float h_im = (float)(ho * s.sh - s.ph + ki * s.dh) + dy;
+    const float w_im = (float)(wo * s.sw - s.pw + kj * s.dw) + dx;
+    int flags = 32;
+    int base = 0;
+    if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {   // dcn_v2_im2col_cuda.cu:286-289
+      const float hf = floorf(h_im), wf = floorf(w_im);
+      const int hl = (int)hf, wl = (int)wf;
+      mt.lh = h_im - hf;
+      mt.lw = w_im - wf;
+      flags |= 16;
+      if (hl >= 0 && wl >= 0) flags |= 1;
+      if (hl >= 0 && wl + 1 <= s.W - 1) flags |= 2;
+      if (hl + 1 <= s.H - 1 && wl >= 0) flags |= 4;
+      if (hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1) flags |= 8;
+      base = hl * s.W + wl + s.W + 1;
+    }
+    mt.packed = (base << 6) | flags;
+  }
+  return mt;
+}
+
+// grid = images x pixel tiles, 8 warps.  Per deformable group the CTA first lays the geometry of its 9 x 128 sampling
+// points into shared memory (every point computed once), then each warp walks (tap, 4 pixels) items with
+// lane = (pixel j, 4-channel quad c4): 16-byte loads of the dcol line and of the four corner lines, next channel
+// block in flight while the current one is reduced.
+__global__ void __launch_bounds__(256, 3)
+k_dcn_bwd_offmask(const float *__restrict__ xt, const float *__restrict__ offset, const float *__restrict__ mask,
+                  const float *__restrict__ dcol, float *__restrict__ dxt, float *__restrict__ goff,
+                  float *__restrict__ gmask, const DcnShapeTc s, const BwdGeom g, const int b_first) {
+  __shared__ BwdMetaTc meta[TC_NT * TC_TP];
+  const int KT = s.kh * s.kw;
+  const long long HWo = (long long)s.Ho * s.Wo, HW = (long long)s.H * s.W;
+  const int Cp = s.nb * TC_CB;
+  const int t = blockIdx.x % g.tiles, bl = blockIdx.x / g.tiles;   // bl: image within this batch chunk (dcol index)
+  const int b = b_first + bl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = lane >> 3, c4 = lane & 7;
+  const int ty0 = (t / s.tiles_x) * s.th, tx0 = (t % s.tiles_x) * s.tw;
+  const int tws = s.tw == 16 ? 4 : 3;                               // tile width is 16 or 8 (fill_shape)
+  const float *off_img = offset + (long long)b * s.off_bs, *mask_img = mask + (long long)b * s.mask_bs;
+  const float *x_img = xt + (long long)b * HW * Cp + c4 * 4;
+  float *dx_img = dxt ? dxt + (long long)b * HW * Cp + c4 * 4 : nullptr;
+  const float *dc_img = dcol + (long long)bl * HWo * g.Qp * TC_CB + c4 * 4;
+  const int xs1 = Cp, xs2 = s.W * Cp, xs3 = (s.W + 1) * Cp;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  struct Lines { float4 d, x1, x2, x3, x4; };
+  for (int gi = 0; gi < s.dg; ++gi) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < KT * TC_TP; idx += 256) {
+      const int tap = idx >> 7, pp = idx & (TC_TP - 1);
+      meta[idx] = bwd_meta(s, off_img, mask_img, gi, tap, ty0 + (pp >> tws), tx0 + (pp & (s.tw - 1)));
+    }
+    __syncthreads();
+    for (int tap = 0; tap < KT; ++tap) {
+#pragma unroll 1
+      for (int pq = warp; pq < TC_TP / 4; pq += 8) {
+        const int pp = pq * 4 + j;
+        const BwdMetaTc mt = meta[tap * TC_TP + pp];
+        const int flags = mt.packed & 63;
+        float am = 0.f, ah = 0.f, aw = 0.f;
+        const long long p = (long long)(ty0 + (pp >> tws)) * s.Wo + tx0 + (pp & (s.tw - 1));
+        if (flags & 16) {
+          const int base = (mt.packed >> 6) - (s.W + 1);
+          const bool f1 = flags & 1, f2 = flags & 2, f3 = flags & 4, f4 = flags & 8;
+          const float lh = mt.lh, lw = mt.lw, hh = 1.f - lh, hw = 1.f - lw, m = mt.m;
+          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+          const float *dc = dc_img + (p * g.Qp + (long long)gi * s.cbs_pg * TC_NT + tap) * TC_CB;
+          const long long xo = (long long)base * Cp + gi * s.cbs_pg * TC_CB;
+          const float *xp = x_img + xo;
+          auto load = [&](int cbi) {
+            Lines L;
+            L.d = __ldg(reinterpret_cast<const float4 *>(dc + cbi * (TC_NT * TC_CB)));
+            const float *xq = xp + cbi * TC_CB;
+            L.x1 = f1 ? __ldg(reinterpret_cast<const float4 *>(xq)) : z4;
+            L.x2 = f2 ? __ldg(reinterpret_cast<const float4 *>(xq + xs1)) : z4;
+            L.x3 = f3 ? __ldg(reinterpret_cast<const float4 *>(xq + xs2)) : z4;
+            L.x4 = f4 ? __ldg(reinterpret_cast<const float4 *>(xq + xs3)) : z4;
+            return L;
+          };
+          Lines cur = load(0);
+          for (int cbi = 0; cbi < s.cbs_pg; ++cbi) {
+            Lines nxt = cur;
+            if (cbi + 1 < s.cbs_pg) nxt = load(cbi + 1);
+            const float4 d = cur.d, x1 = cur.x1, x2 = cur.x2, x3 = cur.x3, x4 = cur.x4;
+            // dMask (:297): dcol * unmasked bilinear sample
+            float4 v;
+            v.x = w1 * x1.x + w2 * x2.x + w3 * x3.x + w4 * x4.x;
+            v.y = w1 * x1.y + w2 * x2.y + w3 * x3.y + w4 * x4.y;
+            v.z = w1 * x1.z + w2 * x2.z + w3 * x3.z + w4 * x4.z;
+            v.w = w1 * x1.w + w2 * x2.w + w3 * x3.w + w4 * x4.w;
+            am += dot4(d, v);
+            // dOffset (:75-116, :299-302): dcol * mask * d(sample)/d{h,w}
+            const float4 dm = make_float4(d.x * m, d.y * m, d.z * m, d.w * m);
+            float4 gh, gw;
+            gh.x = -hw * x1.x - lw * x2.x + hw * x3.x + lw * x4.x;
+            gh.y = -hw * x1.y - lw * x2.y + hw * x3.y + lw * x4.y;
+            gh.z = -hw * x1.z - lw * x2.z + hw * x3.z + lw * x4.z;
+            gh.w = -hw * x1.w - lw * x2.w + hw * x3.w + lw * x4.w;
+            gw.x = -hh * x1.x + hh * x2.x - lh * x3.x + lh * x4.x;
+            gw.y = -hh * x1.y + hh * x2.y - lh * x3.y + lh * x4.y;
+            gw.z = -hh * x1.z + hh * x2.z - lh * x3.z + lh * x4.z;
+            gw.w = -hh * x1.w + hh * x2.w - lh * x3.w + lh * x4.w;
+            ah += dot4(dm, gh);
+            aw += dot4(dm, gw);
+            // dX (:182-239): the four corners receive dcol * mask * corner weight
+            if (dx_img) {
+              float *gx = dx_img + xo + cbi * TC_CB;
+              if (f1 && w1 != 0.f) red_add_v4(gx, dm.x * w1, dm.y * w1, dm.z * w1, dm.w * w1);
+              if (f2 && w2 != 0.f) red_add_v4(gx + xs1, dm.x * w2, dm.y * w2, dm.z * w2, dm.w * w2);
+              if (f3 && w3 != 0.f) red_add_v4(gx + xs2, dm.x * w3, dm.y * w3, dm.z * w3, dm.w * w3);
+              if (f4 && w4 != 0.f) red_add_v4(gx + xs3, dm.x * w4, dm.y * w4, dm.z * w4, dm.w * w4);
+            }
+            cur = nxt;
+          }
+        }
+        // fixed-order reduction over the 8 channel quads of a pixel
+#pragma unroll
+        for (int k = 4; k > 0; k >>= 1) {
+          am += __shfl_xor_sync(0xffffffffu, am, k);
+          ah += __shfl_xor_sync(0xffffffffu, ah, k);
+          aw += __shfl_xor_sync(0xffffffffu, aw, k);
+        }
+        // the gradients arrive zero-filled (dcn_v2_func.py:44-48) and every (tap, pixel) has exactly one writer:
+        // a plain store is the accumulation
+        if ((flags & 32) && c4 == 0) {
+          if (gmask) gmask[(((long long)b * s.dg + gi) * KT + tap) * HWo + p] = am;
+          if (goff) {
+            float *gp = goff + (((long long)b * s.dg + gi) * 2 * KT + 2 * tap) * HWo + p;
+            gp[0] = ah;
+            gp[HWo] = aw;
+          }
+        }
+      }
+    }
+  }
+}
+
+// gx[b][ch][pos] += dxt[b][pos][slot(ch)]   (inverse of k_dcn_nhwc).  grid (pixel blocks of 32, channel blocks of 64, B)
+__global__ void __launch_bounds__(256) k_dcn_bwd_dx_nchw(const float *__restrict__ dxt, float *__restrict__ gx,
+                                                         const DcnShapeTc s) {
+  __shared__ float tile[64][33];
+  const long long HW = (long long)s.H * s.W;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64, b = blockIdx.z;
+  const int Cp = s.nb * TC_CB, cpg = s.Cin / s.dg;
+  {
+    const int c = threadIdx.x & 63, pr = threadIdx.x >> 6;
+    const int ch = c0 + c;
+    if (ch < s.Cin) {
+      const int gi = ch / cpg, within = ch - gi * cpg;
+      const int slot = (gi * s.cbs_pg + within / TC_CB) * TC_CB + within % TC_CB;
+      for (int px = pr; px < 32; px += 4)
+        tile[c][px] = (p0 + px < HW) ? __ldg(dxt + ((long long)b * HW + p0 + px) * Cp + slot) : 0.f;
+    }
+  }
+  __syncthreads();
+  {
+    const int px = threadIdx.x & 31, cr = threadIdx.x >> 5;
+    for (int c = cr; c < 64; c += 8)
+      if (c0 + c < s.Cin && p0 + px < HW) gx[((long long)b * s.Cin + c0 + c) * HW + p0 + px] += tile[c][px];
+  }
+}
+
+// ------------------------------------------------------------------ dW = dY . col^T   (K = pixels)
+constexpr int WG_SAMPLERS = 16;
+constexpr int WG_THREADS = (TC_WARP_S0 + WG_SAMPLERS) * 32;   // warps 0-3 epilogue, 4 MMA, 5 TMA, 6-21 samplers
+
+struct WgGeom {
+  int co_r;          // Cout rounded up to 16 (UMMA N)
+  int spi;           // 32-pixel slices per image
+  int n_slices;      // B * spi
+  int splits;        // pixel-range splits (CTAs per row group)
+  int stages;
+  int stage_bytes;   // 2 * TC_A_BYTES + 2 * co_r * 128
+  unsigned wo_magic; // floor(2^32 / Wo) + 1: p / Wo == umulhi(p, magic) for p < 2^32 / Wo; 0 = divide
+};
+static WgGeom wg_geom(const DcnShapeTc &s, const BwdGeom &g) {
+  WgGeom w;
+  w.co_r = (s.Cout + 15) / 16 * 16;
+  w.spi = (int)(((long long)s.Ho * s.Wo + TC_K - 1) / TC_K);
+  w.n_slices = s.B * w.spi;
+  int splits = (num_sms() + g.RG - 1) / g.RG;
+  if (splits > w.n_slices) splits = w.n_slices;
+  if (splits < 1) splits = 1;
+  w.splits = splits;
+  w.stage_bytes = 2 * TC_A_BYTES + 2 * w.co_r * TC_K * 4;
+  w.stages = w.stage_bytes <= 65536 ? 3 : 2;
+  w.wo_magic = ((unsigned long long)s.Ho * s.Wo * s.Wo < (1ull << 32)) ? (unsigned)((1ull << 32) / (unsigned)s.Wo + 1) : 0u;
+  return w;
+}
+
+// dY [B][Cout][HWo] -> per (image, 32-pixel slice): [co_r rows = output channel][32 k = pixel], hi then lo.  grid (spi, B)
+// A warp owns one output channel of the slice at a time, so the bias gradient's partial sums (dcn_v2_cuda.c:225-230)
+// fall out of the same pass: bpart[slice][o] = sum of the 32 pixels, fixed shuffle order.
+__global__ void __launch_bounds__(256) k_bwd_prep_gyk(const float *__restrict__ gy, const DcnShapeTc s, const WgGeom wg,
+                                                      float *__restrict__ gyk, float *__restrict__ bpart) {
+  const int sl = blockIdx.x, b = blockIdx.y;
+  const long long HWo = (long long)s.Ho * s.Wo, p0 = (long long)sl * TC_K;
+  const size_t tile = (size_t)wg.co_r * TC_K;
+  unsigned char *hi = reinterpret_cast<unsigned char *>(gyk + ((size_t)b * wg.spi + sl) * 2 * tile);
+  unsigned char *lo = hi + tile * 4;
+  for (int i = threadIdx.x; i < wg.co_r * TC_K; i += blockDim.x) {
+    const int k = i & (TC_K - 1), o = i >> 5;
+    const float v = (o < s.Cout && p0 + k < HWo) ? __ldg(gy + ((long long)b * s.Cout + o) * HWo + p0 + k) : 0.f;
+    const float h = tf32_hi(v);
+    *reinterpret_cast<float *>(hi + tc_tile_off(o, k)) = h;
+    *reinterpret_cast<float *>(lo + tc_tile_off(o, k)) = v - h;
+    if (bpart) {
+      float sum = v;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      if (k == 0) bpart[((size_t)b * wg.spi + sl) * wg.co_r + o] = sum;
+    }
+  }
+}
+
+// gb[o] += sum over slices of bpart[slice][o]: strided per-thread sums, then a fixed tree.  grid = Cout
+__global__ void __launch_bounds__(256) k_dcn_bwd_bias_reduce(const float *__restrict__ bpart, float *__restrict__ gb,
+                                                             const WgGeom wg) {
+  __shared__ float red[256];
+  const int o = blockIdx.x;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < wg.n_slices; i += 256) sum += __ldg(bpart + (size_t)i * wg.co_r + o);
+  red[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gb[o] += red[0];
+}
+
+// CTA = (row group rg = 4 chunks x 32 channels, split): D[128 rows][Cout] accumulates over the CTA's slices in TMEM.
+__global__ void __launch_bounds__(WG_THREADS, 1)
+k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offset, const float *__restrict__ mask,
+                    const float *__restrict__ gyk, float *__restrict__ wpart, const DcnShapeTc s, const BwdGeom g,
+                    const WgGeom wg) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ __align__(8) uint64_t a_full[3], b_full[3], empty[3], tm_full;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rg = blockIdx.x % g.RG, split = blockIdx.x / g.RG;
+  const int sl0 = (int)((long long)split * wg.n_slices / wg.splits), sl1 = (int)((long long)(split + 1) * wg.n_slices / wg.splits);
+  const int KT = s.kh * s.kw;
+  const long long HWo = (long long)s.Ho * s.Wo, HW = (long long)s.H * s.W;
+  const int Cp = s.nb * TC_CB;
+  const int b_bytes = wg.co_r * TC_K * 4;
+
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], WG_SAMPLERS); mbar_init(&b_full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&tm_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == TC_WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+
+  if (warp >= TC_WARP_S0) {
+    // =========================================================== samplers: the masked column tile, rows = channels
+    const int sw = warp - TC_WARP_S0;
+    const int j = lane >> 3, c4 = lane & 7;       // gather: lane = (pixel j of 4, channel quad c4): one line per quarter-warp
+    const int rj = lane & 3, rc4 = lane >> 2;     // store:  lane = (channel c4' * 4 + j'): 8 consecutive rows per quarter-warp
+    const bool sel1 = rj & 1, sel2 = rj & 2;
+    // per-task constants (task = sw + 16 it: chunk ql = task / 8, pixel group pg = task % 8)
+    bool t_ok[2];
+    int t_pp[2], t_hb[2], t_wb[2];
+    const float *t_off[2], *t_msk[2], *t_x[2];
+    uint32_t t_dst[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int task = sw + it * WG_SAMPLERS;
+      const int ql = task >> 3, pg = task & 7;
+      const int q = rg * 4 + ql;
+      const int bi = q / TC_NT, tap = q - bi * TC_NT;
+      const int gi = bi / s.cbs_pg;
+      const int ki = tap / s.kw, kj = tap - ki * s.kw;
+      t_ok[it] = q < g.Q && tap < KT;
+      t_pp[it] = pg * 4 + j;
+      t_hb[it] = ki * s.dh - s.ph;
+      t_wb[it] = kj * s.dw - s.pw;
+      t_off[it] = offset + ((long long)gi * 2 * KT + 2 * tap) * HWo;
+      t_msk[it] = mask + ((long long)gi * KT + tap) * HWo;
+      t_x[it] = xt + bi * TC_CB + c4 * 4;
+      t_dst[it] = tc_tile_off(ql * 32 + rc4 * 4 + rj, pg * 4);
+    }
+    const int HWo_i = (int)HWo;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int stage = 0, ph = 0;
+    int b = sl0 / wg.spi, sll = sl0 - b * wg.spi;      // image and slice within the image
+    // offsets / mask of the first slice; afterwards they are fetched one slice ahead
+    float pdy[2], pdx[2], pm[2];
+    auto fetch = [&](int bb, int sl_local) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int p = sl_local * TC_K + t_pp[it];
+        pdy[it] = pdx[it] = pm[it] = 0.f;
+        if (t_ok[it] && p < HWo_i) {
+          pdy[it] = __ldg(t_off[it] + (long long)bb * s.off_bs + p);
+          pdx[it] = __ldg(t_off[it] + (long long)bb * s.off_bs + HWo + p);
+          pm[it] = __ldg(t_msk[it] + (long long)bb * s.mask_bs + p);
+        }
+      }
+    };
+    if (sl0 < sl1) fetch(b, sll);
+    for (int sl = sl0; sl < sl1; ++sl) {
+      float dy[2], dx[2], m[2];
+#pragma unroll
+      for (int it = 0; it < 2; ++it) { dy[it] = pdy[it]; dx[it] = pdx[it]; m[it] = pm[it]; }
+      int nb_ = b, nsl = sll + 1;
+      if (nsl == wg.spi) { nsl = 0; ++nb_; }
+      if (sl + 1 < sl1) fetch(nb_, nsl);
+      float4 val[2];
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int p = sll * TC_K + t_pp[it];
+        float4 v = z4;
+        if (t_ok[it] && p < HWo_i) {
+          const int ho = wg.wo_magic ? (int)__umulhi((unsigned)p, wg.wo_magic) : p / s.Wo;
+          const int wo = p - ho * s.Wo;
+          const float h_im = (float)(ho * s.sh + t_hb[it]) + dy[it];
+          const float w_im = (float)(wo * s.sw + t_wb[it]) + dx[it];
+          if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {   // dcn_v2_im2col_cuda.cu:165
+            const float hf = floorf(h_im), wf = floorf(w_im);
+            const int hl = (int)hf, wl = (int)wf;
+            const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+            const float *xb = t_x[it] + ((long long)b * HW + (long long)hl * s.W + wl) * Cp;
+            const bool f1 = hl >= 0 && wl >= 0, f2 = hl >= 0 && wl + 1 <= s.W - 1;
+            const bool f3 = hl + 1 <= s.H - 1 && wl >= 0, f4 = hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1;
+            const float4 x1 = f1 ? __ldg(reinterpret_cast<const float4 *>(xb)) : z4;
+            const float4 x2 = f2 ? __ldg(reinterpret_cast<const float4 *>(xb + Cp)) : z4;
+            const float4 x3 = f3 ? __ldg(reinterpret_cast<const float4 *>(xb + (long long)s.W * Cp)) : z4;
+            const float4 x4 = f4 ? __ldg(reinterpret_cast<const float4 *>(xb + (long long)(s.W + 1) * Cp)) : z4;
+            const float mm = m[it];
+            const float w1 = hh * hw * mm, w2 = hh * lw * mm, w3 = lh * hw * mm, w4 = lh * lw * mm;   // as the forward sampler
+            v.x = fmaf(w4, x4.x, fmaf(w3, x3.x, fmaf(w2, x2.x, w1 * x1.x)));
+            v.y = fmaf(w4, x4.y, fmaf(w3, x3.y, fmaf(w2, x2.y, w1 * x1.y)));
+            v.z = fmaf(w4, x4.z, fmaf(w3, x3.z, fmaf(w2, x2.z, w1 * x1.z)));
+            v.w = fmaf(w4, x4.w, fmaf(w3, x3.w, fmaf(w2, x2.w, w1 * x1.w)));
+          }
+        }
+        val[it] = v;
+      }
+      mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
+      unsigned char *a_hi = tc_smem + (size_t)stage * wg.stage_bytes;
+      unsigned char *a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        // 4x4 transpose across the lanes of one channel quad: this lane ends up with channel rc4*4+rj of pixels 0..3
+        float u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int src = i * 8 + rc4;
+          const float t0 = __shfl_sync(0xffffffffu, val[it].x, src), t1 = __shfl_sync(0xffffffffu, val[it].y, src);
+          const float t2 = __shfl_sync(0xffffffffu, val[it].z, src), t3 = __shfl_sync(0xffffffffu, val[it].w, src);
+          const float lo01 = sel1 ? t1 : t0, hi23 = sel1 ? t3 : t2;
+          u[i] = sel2 ? hi23 : lo01;
+        }
+        const float4 h4 = make_float4(tf32_hi(u[0]), tf32_hi(u[1]), tf32_hi(u[2]), tf32_hi(u[3]));
+        *reinterpret_cast<float4 *>(a_hi + t_dst[it]) = h4;
+        *reinterpret_cast<float4 *>(a_lo + t_dst[it]) = make_float4(u[0] - h4.x, u[1] - h4.y, u[2] - h4.z, u[3] - h4.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_tc(&a_full[stage]);
+      if (++stage == wg.stages) { stage = 0; ph ^= 1; }
+      b = nb_;
+      sll = nsl;
+    }
+  } else if (warp == TC_WARP_TMA) {
+    if (lane == 0) {
+      int stage = 0, ph = 0;
+      for (int sl = sl0; sl < sl1; ++sl) {
+        mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
+        unsigned char *dst = tc_smem + (size_t)stage * wg.stage_bytes + 2 * TC_A_BYTES;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(gyk) + (size_t)sl * 2 * b_bytes;
+        mbar_expect_tx(&b_full[stage], 2u * (uint32_t)b_bytes);
+        for (uint32_t off = 0; off < 2u * (uint32_t)b_bytes; off += 2048u) bulk_g2s(dst + off, src + off, 2048u, &b_full[stage]);
+        if (++stage == wg.stages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == TC_WARP_MMA) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(wg.co_r >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0, ph = 0;
+      for (int sl = sl0; sl < sl1; ++sl) {
+        mbar_wait(&a_full[stage], (uint32_t)ph);
+        mbar_wait(&b_full[stage], (uint32_t)ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ah = smem_u32(tc_smem + (size_t)stage * wg.stage_bytes), al = ah + TC_A_BYTES;
+        const uint32_t bh = al + TC_A_BYTES, bl = bh + (uint32_t)b_bytes;
+#pragma unroll
+        for (int k8 = 0; k8 < TC_K / 8; ++k8) {
+          const uint32_t koff = (uint32_t)k8 * 2u * TC_LBO;
+          const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
+          const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
+          umma_tf32(tm, dal, dbh, idesc, (sl > sl0 || k8 > 0) ? 1u : 0u);
+          umma_tf32(tm, dah, dbl, idesc, 1u);
+          umma_tf32(tm, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == wg.stages) { stage = 0; ph ^= 1; }
+      }
+      umma_commit(&tm_full);
+    }
+  } else {
+    // epilogue: TMEM lane = row (chunk, channel), columns = output channels -> wpart[split][rg][row][co_r]
+    const int qw = warp;
+    float *dst = wpart + (((size_t)split * g.RG + rg) * 128 + qw * 32 + lane) * wg.co_r;
+    if (sl1 > sl0) {
+      mbar_wait(&tm_full, 0u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint32_t taddr = tm + ((uint32_t)(qw * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < wg.co_r; c0 += 32) {
+      uint32_t v[32];
+      if (sl1 > sl0) {
+        tmem_ld32(taddr + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        if (c0 + i < wg.co_r)
+          *reinterpret_cast<float4 *>(dst + c0 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                   __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == TC_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(256));
+}
+
+// gw[o][ch][tap] += sum over splits (ascending) of wpart[split][rg][row][o]
+__global__ void __launch_bounds__(256) k_dcn_bwd_wreduce(const float *__restrict__ wpart, float *__restrict__ gw,
+                                                         const DcnShapeTc s, const BwdGeom g, const WgGeom wg) {
+  const int KT = s.kh * s.kw, cpg = s.Cin / s.dg;
+  const long long total = (long long)g.RG * 128 * wg.co_r;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % wg.co_r);
+    const int row = (int)((i / wg.co_r) % 128), rg = (int)(i / ((long long)wg.co_r * 128));
+    const int q = rg * 4 + (row >> 5), ch = row & 31;
+    const int bi = q / TC_NT, tap = q - bi * TC_NT;
+    const int gi = bi / s.cbs_pg, cw = (bi - gi * s.cbs_pg) * TC_CB + ch;
+    if (q >= g.Q || o >= s.Cout || cw >= cpg || tap >= KT) continue;
+    float acc = 0.f;
+    for (int sp = 0; sp < wg.splits; ++sp) acc += __ldg(wpart + (size_t)sp * total + i);
+    gw[((size_t)o * s.Cin + gi * cpg + cw) * KT + tap] += acc;
+  }
+}
+
+// ------------------------------------------------------------------ host
+static size_t bw_xt_bytes(const DcnShapeTc &s) { return align_up((size_t)s.B * s.H * s.W * s.nb * TC_CB * 4, 256); }
+static size_t bw_wtt_bytes(const BwdGeom &g) { return align_up((size_t)g.RG * g.KS * BW_TILE_FLOATS * 4, 256); }
+static size_t bw_gyt_bytes_per_image(const BwdGeom &g) { return (size_t)g.tiles * g.KS * BW_TILE_FLOATS * 4; }
+static size_t bw_dcol_bytes_per_image(const DcnShapeTc &s, const BwdGeom &g) {
+  return align_up((size_t)s.Ho * s.Wo * g.Qp * TC_CB * 4, 256);
+}
+// images per pass: the column gradient of a pass is held to ~1.5 GiB (B=16 of the largest dla_34 layer is 0.67 GB)
+static int bw_batch_chunk(const DcnShapeTc &s, const BwdGeom &g) {
+  const size_t per = bw_dcol_bytes_per_image(s, g) + bw_gyt_bytes_per_image(g);
+  long long bc = (long long)((1536ull << 20) / per);
+  if (bc < 1) bc = 1;
+  if (bc > s.B) bc = s.B;
+  return (int)bc;
+}
+
+static size_t bw_gyk_bytes(const WgGeom &wg) { return align_up((size_t)wg.n_slices * 2 * wg.co_r * TC_K * 4, 256); }
+static size_t bw_wpart_bytes(const BwdGeom &g, const WgGeom &wg) {
+  return align_up((size_t)wg.splits * g.RG * 128 * wg.co_r * 4, 256);
+}
+static size_t bw_bpart_bytes(const WgGeom &wg) { return align_up((size_t)wg.n_slices * wg.co_r * 4, 256); }
+
+// [xt][dxt][wtt][ max( gyt + dcol of one batch chunk , gyk + wpart ) ]: the data and the weight passes run one after
+// the other on the stream and share the tail
+size_t dcn_tc_bwd_workspace_bytes(int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int ph, int dh, int dg) {
+  DcnShapeTc s;
+  fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sh, ph, ph, dh, dh, dg);
+  const BwdGeom g = bwd_geom(s);
+  const WgGeom wg = wg_geom(s, g);
+  const int bc = bw_batch_chunk(s, g);
+  const size_t data = align_up((size_t)bc * bw_gyt_bytes_per_image(g), 256) + (size_t)bc * bw_dcol_bytes_per_image(s, g);
+  const size_t wgt = bw_gyk_bytes(wg) + bw_wpart_bytes(g, wg) + bw_bpart_bytes(wg);
+  return 2 * bw_xt_bytes(s) + bw_wtt_bytes(g) + (data > wgt ? data : wgt);
+}
+
+// dX, dOffset, dMask (each nullable; accumulated into, as cnb_dcnv2_backward documents).
+int dcn_backward_data_tc(const float *input, const float *offset, const float *mask, const float *weight,
+                         const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask, int b,
+                         int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                         int dg, void *workspace, cudaStream_t stream, int xt_ready) {
+  DcnShapeTc s;
+  fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
+  const BwdGeom g = bwd_geom(s);
+  const int bc = bw_batch_chunk(s, g);
+  char *wp = reinterpret_cast<char *>(workspace);
+  float *xt = reinterpret_cast<float *>(wp);  wp += bw_xt_bytes(s);
+  float *dxt = reinterpret_cast<float *>(wp); wp += bw_xt_bytes(s);
+  float *wtt = reinterpret_cast<float *>(wp); wp += bw_wtt_bytes(g);
+  float *gyt = reinterpret_cast<float *>(wp); wp += align_up((size_t)bc * bw_gyt_bytes_per_image(g), 256);
+  float *dcol = reinterpret_cast<float *>(wp);
+  const long long HW = (long long)h * w, HWo = (long long)s.Ho * s.Wo;
+
+  int rc = CNB_OK;
+  if (!xt_ready) rc = dcn_to_channels_last(input, xt, s, stream);
+  if (rc != CNB_OK) return rc;
+  if (grad_input) CNB_CUDA(cudaMemsetAsync(dxt, 0, (size_t)b * HW * s.nb * TC_CB * 4, stream));
+  k_bwd_prep_w<<<g.RG * g.KS, 256, 0, stream>>>(weight, s, g, wtt);
+  CNB_CHECK_LAUNCH("cnb_dcnv2_backward weight tiles");
+  count_launch();
+  const size_t smem = (size_t)BW_STAGES * BW_STAGE_BYTES;
+  static thread_local int dev_done = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev_done != dev) {
+    CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_dcol_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dev_done = dev;
+  }
+  for (int b0 = 0; b0 < b; b0 += bc) {
+    const int nbimg = (b - b0 < bc) ? b - b0 : bc;
+    dim3 pgrid((unsigned)g.tiles, (unsigned)g.KS, (unsigned)nbimg);
+    k_bwd_prep_gy<<<pgrid, 256, 0, stream>>>(grad_output + (long long)b0 * cout * HWo, s, g, gyt);
+    CNB_CHECK_LAUNCH("cnb_dcnv2_backward grad_output tiles");
+    const int n_items = nbimg * g.tiles * g.RG;
+    const int grid = n_items < num_sms() ? n_items : num_sms();
+    k_dcn_bwd_dcol_tc<<<grid, BW_THREADS, smem, stream>>>(gyt, wtt, dcol, s, g, n_items);
+    CNB_CHECK_LAUNCH("cnb_dcnv2_backward column gradient (tcgen05)");
+    k_dcn_bwd_offmask<<<nbimg * g.tiles, 256, 0, stream>>>(xt, offset, mask, dcol, grad_input ? dxt : nullptr, grad_offset,
+                                                           grad_mask, s, g, b0);
+    CNB_CHECK_LAUNCH("cnb_dcnv2_backward offset/mask gradient");
+    count_launch(3);
+  }
+  if (grad_input) {
+    dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((cin + 63) / 64), (unsigned)b);
+    k_dcn_bwd_dx_nchw<<<tgrid, 256, 0, stream>>>(dxt, grad_input, s);
+    CNB_CHECK_LAUNCH("cnb_dcnv2_backward input gradient");
+    count_launch();
+  }
+  return CNB_OK;
+}
+
+// dW and dBias (accumulated into grad_weight / grad_bias; grad_bias nullable).  xt_ready != 0: the channels-last input copy at the head of the workspace was
+// already written by dcn_backward_data_tc on this stream.
+int dcn_backward_weight_tc(const float *input, const float *offset, const float *mask, const float *grad_output,
+                           float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw,
+                           int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream, int xt_ready) {
+  DcnShapeTc s;
+  fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
+  const BwdGeom g = bwd_geom(s);
+  const WgGeom wg = wg_geom(s, g);
+  char *wp = reinterpret_cast<char *>(workspace);
+  float *xt = reinterpret_cast<float *>(wp);  wp += 2 * bw_xt_bytes(s) + bw_wtt_bytes(g);
+  float *gyk = reinterpret_cast<float *>(wp); wp += bw_gyk_bytes(wg);
+  float *wpart = reinterpret_cast<float *>(wp); wp += bw_wpart_bytes(g, wg);
+  float *bpart = reinterpret_cast<float *>(wp);
+  if (!xt_ready) {
+    const int rc = dcn_to_channels_last(input, xt, s, stream);
+    if (rc != CNB_OK) return rc;
+  }
+  dim3 pgrid((unsigned)wg.spi, (unsigned)b);
+  k_bwd_prep_gyk<<<pgrid, 256, 0, stream>>>(grad_output, s, wg, gyk, grad_bias ? bpart : nullptr);
+  CNB_CHECK_LAUNCH("cnb_dcnv2_backward grad_output tiles (weight pass)");
+  const size_t smem = (size_t)wg.stages * wg.stage_bytes;
+  static thread_local int dev_done = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev_done != dev) {
+    CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_weight_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536));
+    dev_done = dev;
+  }
+  k_dcn_bwd_weight_tc<<<g.RG * wg.splits, WG_THREADS, smem, stream>>>(xt, offset, mask, gyk, wpart, s, g, wg);
+  CNB_CHECK_LAUNCH("cnb_dcnv2_backward weight gradient (tcgen05)");
+  const long long total = (long long)g.RG * 128 * wg.co_r;
+  k_dcn_bwd_wreduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(wpart, grad_weight, s, g, wg);
+  CNB_CHECK_LAUNCH("cnb_dcnv2_backward weight gradient reduce");
+  count_launch(3);
+  if (grad_bias) {
+    k_dcn_bwd_bias_reduce<<<cout, 256, 0, stream>>>(bpart, grad_bias, wg);
+    CNB_CHECK_LAUNCH("cnb_dcnv2_backward bias gradient reduce");
+    count_launch();
+  }
+  return CNB_OK;
+}
+
+}  // namespace cnb

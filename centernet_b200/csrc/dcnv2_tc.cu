@@ -31,65 +31,9 @@
 // The weight tiles are pre-split / pre-tiled by k_dcn_prep_weights: once per call through the plain
 // cnb_dcnv2_forward, or once per weight version through cnb_dcnv2_prepare_weights +
 // cnb_dcnv2_forward_prepared (what the Python module does).
-#include "common.cuh"
+#include "dcnv2_tc.cuh"
 
 namespace cnb {
-
-constexpr int TC_TP = 128;        // pixels per item (UMMA M)
-constexpr int TC_CB = 32;         // input channels per chunk = one 128-byte line of the channels-last copy
-constexpr int TC_NT = 9;          // taps (3x3 kernel; fewer taps leave zero weight tiles)
-constexpr int TC_K = TC_CB;       // K per chunk
-constexpr int TC_KC = TC_K / 4;   // 16-byte k-chunks
-constexpr int TC_EPI_WARPS = 4;   // warps 0-3: TMEM lane quarter = warp index
-constexpr int TC_WARP_MMA = 4;
-constexpr int TC_WARP_TMA = 5;
-constexpr int TC_WARP_S0 = 6;     // first sampler warp
-constexpr int TC_SAMPLERS = 16;   // sampler warps: 2 warp items (4 pixels each) per warp and chunk
-constexpr int TC_THREADS = (TC_WARP_S0 + TC_SAMPLERS) * 32;   // 704
-constexpr uint32_t TC_LBO = 128;            // bytes between consecutive k-chunks (one 8 x 16 B core matrix)
-constexpr uint32_t TC_SBO = TC_KC * 128;    // bytes between 8-row groups
-constexpr int TC_A_BYTES = TC_TP * TC_K * 4;  // 16384 per hi / lo tile
-
-struct DcnShapeTc {
-  int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo;
-  int co_t;       // output channels per item (64 or 128)
-  int n_cot;      // Cout tiles
-  int cbs_pg;     // 32-channel blocks per deformable group
-  int nb;         // channel blocks in total = dg * cbs_pg
-  int tw, th;     // pixel tile (tw * th == 128)
-  int tiles_x, tiles_y;
-  int splits;     // K splits (channel-block ranges) per item; > 1 -> partial sums + k_dcn_reduce
-  int n_items;    // B * tiles * n_cot * splits
-  // fused prologue / epilogue (N3, dcn_v2.py:64-70 + pose_dla_dcn.py:345-357)
-  long long off_bs, mask_bs;   // batch strides (floats) of the offset / mask tensors
-  int mask_logit;              // mask holds the raw conv_offset_mask output: sigmoid applied on the fly
-  int relu;                    // epilogue: y = relu(scale[o] * (acc + bias[o]) + shift[o])
-  const float *epi_scale, *epi_shift;   // folded inference BatchNorm (nullable)
-};
-
-struct __align__(16) TapMetaTc {
-  int o[4];
-  float w[4];
-};
-
-__device__ __forceinline__ uint32_t tc_tile_off(int row, int k) {  // byte offset of element (row, k) in a K-major tile
-  return (uint32_t)(row >> 3) * TC_SBO + (uint32_t)(k >> 2) * TC_LBO + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 3) * 4u;
-}
-__device__ __forceinline__ uint64_t tc_desc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fff);
-  d |= (uint64_t)((TC_LBO >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((TC_SBO >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout_type 0 = no swizzle
-  return d;
-}
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-__device__ __forceinline__ void mbar_arrive_tc(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // W[Cout][Cin][KT] -> per (cout tile, channel block bi, tap): hi tile then lo tile, each [co_t][32] in the UMMA
 // layout; k = channel within the block.  Tile index = (cot * nb + bi) * 9 + tap.
@@ -435,39 +379,6 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
   if (warp == TC_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(2 * CO_T));
 }
 
-static void fill_shape(DcnShapeTc *s, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph,
-                       int pw, int dh, int dw, int dg) {
-  s->B = b; s->Cin = cin; s->H = h; s->W = w; s->Cout = cout; s->kh = kh; s->kw = kw; s->sh = sh; s->sw = sw;
-  s->ph = ph; s->pw = pw; s->dh = dh; s->dw = dw; s->dg = dg;
-  s->Ho = (h + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
-  s->Wo = (w + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
-  s->co_t = cout > 64 ? 128 : 64;
-  s->n_cot = (cout + s->co_t - 1) / s->co_t;
-  const int cpg = cin / dg;
-  s->cbs_pg = (cpg + TC_CB - 1) / TC_CB;
-  s->nb = dg * s->cbs_pg;
-  s->tw = s->Wo >= 12 ? 16 : 8;          // 8 x 16 pixel tiles; 16 x 8 on narrow maps
-  s->th = TC_TP / s->tw;
-  s->tiles_x = (s->Wo + s->tw - 1) / s->tw;
-  s->tiles_y = (s->Ho + s->th - 1) / s->th;
-  const long long base_items = (long long)b * s->tiles_x * s->tiles_y * s->n_cot;
-  int splits = 1;
-  const int sms = num_sms();
-  if (base_items < sms) {                 // small maps: split the channel blocks so every SM gets an item
-    splits = (int)((sms + base_items - 1) / base_items);
-    if (splits > s->nb) splits = s->nb;
-    if (splits > 8) splits = 8;
-    if (splits < 1) splits = 1;
-  }
-  s->splits = splits;
-  s->n_items = (int)(base_items * splits);
-  s->off_bs = (long long)dg * 2 * kh * kw * s->Ho * s->Wo;
-  s->mask_bs = (long long)dg * kh * kw * s->Ho * s->Wo;
-  s->mask_logit = 0;
-  s->relu = 0;
-  s->epi_scale = s->epi_shift = nullptr;
-}
-
 size_t dcn_tc_wtiles_bytes(int cin, int cout, int dg) {
   DcnShapeTc s;
   fill_shape(&s, 1, cin, 8, 8, cout, 3, 3, 1, 1, 1, 1, 1, 1, dg);
@@ -495,6 +406,17 @@ int dcn_prepare_weights_tc(const float *weight, int cin, int cout, int kh, int k
   fill_shape(&s, 1, cin, 8, 8, cout, kh, kw, 1, 1, 1, 1, 1, 1, dg);
   k_dcn_prep_weights<<<s.n_cot * s.nb * TC_NT, 256, 0, stream>>>(weight, s, wtiles);
   CNB_CHECK_LAUNCH("cnb_dcnv2 weight tiles");
+  count_launch();
+  return CNB_OK;
+}
+
+int dcn_to_channels_last(const float *x, float *xt, const DcnShapeTc &s, cudaStream_t stream) {
+  const long long HW = (long long)s.H * s.W;
+  if ((s.Cin / s.dg) % TC_CB != 0)   // pad slots of the last channel block of every group must read as zero
+    CNB_CUDA(cudaMemsetAsync(xt, 0, (size_t)s.B * HW * s.nb * TC_CB * 4, stream));
+  dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((s.Cin + 63) / 64), (unsigned)s.B);
+  k_dcn_nhwc<<<tgrid, 256, 0, stream>>>(x, xt, s);
+  CNB_CHECK_LAUNCH("cnb_dcnv2 channels-last copy");
   count_launch();
   return CNB_OK;
 }
@@ -541,12 +463,8 @@ int dcn_forward_tc_prepared(const float *input, int input_nhwc, const float *off
   if (input_nhwc && (cin / dg) % TC_CB == 0) {
     xsrc = input;
   } else {
-    if ((cin / dg) % TC_CB != 0)   // pad slots of the last channel block of every group must read as zero
-      CNB_CUDA(cudaMemsetAsync(xt, 0, (size_t)b * HW * s.nb * TC_CB * 4, stream));
-    dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((cin + 63) / 64), (unsigned)b);
-    k_dcn_nhwc<<<tgrid, 256, 0, stream>>>(input, xt, s);
-    CNB_CHECK_LAUNCH("cnb_dcnv2_forward channels-last copy");
-    count_launch();
+    const int rc_t = dcn_to_channels_last(input, xt, s, stream);
+    if (rc_t != CNB_OK) return rc_t;
   }
   int rc;
   if (s.co_t == 64) rc = launch_fwd<64, 3>(xsrc, offset, mask, wtiles, bias, output, part, s, stream);

@@ -106,9 +106,14 @@ class _DCNv2(Function):
         gmsk = torch.zeros_like(msk)
         gw = torch.zeros_like(w)
         gb = torch.zeros_like(b) if b is not None else None
+        ws, wsb = 0, 0
+        if not _FORCE_FP32:
+            wsb = C.dcnv2_backward_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding, dilation, dg)
+            if wsb:
+                ws = ptr(workspace(wsb, x.device))
         C.dcnv2_backward(ptr(x), ptr(off), ptr(msk), ptr(w), ptr(go), ptr(gx), ptr(goff), ptr(gmsk), ptr(gw), ptr(gb),
                          n, cin, h, wd, cout, kh, kw, stride, stride, padding, padding, dilation, dilation, dg,
-                         0, 0, stream_ptr(x))
+                         ws, wsb, stream_ptr(x))
         return gx, goff, gmsk, gw, gb, None, None, None, None
 
 

@@ -208,7 +208,11 @@ int cnb_reg_loss(const float *output, const void *mask, const int64_t *ind, cons
  * maps too small to fill the GPU, split-K partial sums; the query returns 0 for
  * kernels with more than 9 taps.  workspace == NULL (or smaller than the query,
  * or anisotropic stride/pad/dilation) selects the fp32 CUDA-core forward instead.
- * cnb_dcnv2_backward ignores its workspace arguments (kept for ABI stability). */
+ * cnb_dcnv2_backward: with a workspace of cnb_dcnv2_backward_workspace_bytes (16-byte aligned; channels-last
+ * copies of the input and of dX, TF32 hi/lo tiles of grad_output and of the weights, the column gradient of
+ * up to ~1.5 GiB worth of images at a time) the contractions run on the tensor cores; workspace == NULL (or
+ * smaller, or anisotropic stride/pad/dilation, or more than 9 taps -- the query then returns 0) selects the
+ * fp32 CUDA-core backward. */
 size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
                                  int stride, int pad, int dil, int dg);
 int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask,
@@ -246,6 +250,8 @@ int cnb_dcnv2_forward_fused(const float *input, int input_channels_last, const f
                             int b, int cin, int h, int w, int cout, int kh, int kw,
                             int stride, int pad, int dil, int deformable_groups,
                             void *workspace, size_t workspace_bytes, void *stream);
+size_t cnb_dcnv2_backward_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
+                                          int stride, int pad, int dil, int dg);
 int cnb_dcnv2_backward(const float *input, const float *offset, const float *mask,
                        const float *weight, const float *grad_output,
                        float *grad_input, float *grad_offset, float *grad_mask,

@@ -79,6 +79,45 @@ def test_backward_vs_oracle_autograd(B, Ci, H, W, Co, dg, stride):
         assert err <= 1e-3 * scale, (name, err, scale)      # fp32 gradcheck tolerance of test.py:115 (atol 1e-3)
 
 
+def _raw_backward(x, off, m, w, go, stride, dg, tensor_cores):
+    from centernet_b200._lib import C, ptr, stream_ptr, workspace
+    B, Ci, H, W = x.shape
+    Co = w.shape[0]
+    grads = [torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(m), torch.zeros_like(w),
+             torch.zeros(Co, device=x.device)]
+    ws, wsb, keep = 0, 0, None
+    if tensor_cores:
+        wsb = C.dcnv2_backward_workspace_bytes(B, Ci, Co, H, W, 3, 3, stride, 1, 1, dg)
+        assert wsb > 0
+        keep = workspace(wsb, x.device)
+        ws = ptr(keep)
+    C.dcnv2_backward(ptr(x), ptr(off), ptr(m), ptr(w), ptr(go), *[ptr(g) for g in grads], B, Ci, H, W, Co, 3, 3,
+                     stride, stride, 1, 1, 1, 1, dg, ws, wsb, stream_ptr(x))
+    torch.cuda.synchronize()
+    return grads
+
+
+@pytest.mark.parametrize("B,Ci,H,W,Co,dg,stride", [(2, 64, 40, 48, 64, 1, 1), (3, 96, 17, 23, 40, 1, 1), (2, 128, 16, 16, 272, 1, 1),
+                                                    (2, 64, 16, 24, 64, 2, 1), (2, 40, 19, 21, 24, 1, 2)])
+def test_backward_tensor_core_vs_fp32_path(B, Ci, H, W, Co, dg, stride):
+    """cnb_dcnv2_backward with the workspace (tcgen05, 3xTF32) against the same call without it (fp32 CUDA cores) on
+    shapes the reference-pinned cases do not reach: ragged tiles, channel blocks with padding, Cout > 256 (dW falls
+    back to fp32), two deformable groups, stride 2; and the deterministic part of the tensor-core path repeats."""
+    x, off, m, w, _ = [t.cuda() for t in make(B, Ci, H, W, Co, dg, stride, seed=11, off_scale=1.5)]
+    Ho = (H + 2 - 3) // stride + 1; Wo = (W + 2 - 3) // stride + 1
+    go = torch.randn(B, Co, Ho, Wo, generator=torch.Generator().manual_seed(5)).cuda()
+    a = _raw_backward(x, off, m, w, go, stride, dg, True)
+    a2 = _raw_backward(x, off, m, w, go, stride, dg, True)
+    r = _raw_backward(x, off, m, w, go, stride, dg, False)
+    for name, u, v in zip(("input", "offset", "mask", "weight", "bias"), a, r):
+        scale = max(1.0, v.abs().max().item())
+        assert (u - v).abs().max().item() <= 2e-4 * scale, (name, (u - v).abs().max().item(), scale)
+    for name, u, v in zip(("offset", "mask", "weight", "bias"), a[1:], a2[1:]):
+        if name == "weight" and Co > 256:
+            continue      # fp32 fallback: atomics
+        assert torch.equal(u, v), name + " not bit-identical run to run"
+
+
 def test_dcn_module_and_state_dict_names():
     from centernet_b200.dcn_v2 import DCN
     dcn = DCN(16, 8, kernel_size=(3, 3), stride=1, padding=1, deformable_groups=1).cuda()

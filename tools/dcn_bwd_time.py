@@ -1,0 +1,65 @@
+"""Times cnb_dcnv2_backward on the dla_34 DCN layer shapes (B=16): tensor-core path (with workspace) vs the fp32
+CUDA-core path (workspace = NULL), checks the two against each other and that dOffset / dMask / dW of the
+tensor-core path are bit-identical run to run.  GPU only."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from centernet_b200._lib import C, ptr, stream_ptr, workspace
+
+LAYERS = [(16, 64, 128, 128, 64), (16, 128, 64, 64, 128), (16, 256, 32, 32, 256), (16, 512, 16, 16, 256),
+          (16, 128, 64, 64, 64), (16, 256, 32, 32, 128)]
+
+
+def run(x, off, m, w, go, tc):
+    B, Ci, H, W = x.shape
+    Co = w.shape[0]
+    gx = torch.zeros_like(x); goff = torch.zeros_like(off); gm = torch.zeros_like(m)
+    gw = torch.zeros_like(w); gb = torch.zeros(Co, device=x.device)
+    ws, wsb = 0, 0
+    if tc:
+        wsb = C.dcnv2_backward_workspace_bytes(B, Ci, Co, H, W, 3, 3, 1, 1, 1, 1)
+        wsbuf = workspace(wsb, x.device); ws = ptr(wsbuf)
+    C.dcnv2_backward(ptr(x), ptr(off), ptr(m), ptr(w), ptr(go), ptr(gx), ptr(goff), ptr(gm), ptr(gw), ptr(gb),
+                     B, Ci, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, ws, wsb, stream_ptr(x))
+    return gx, goff, gm, gw, gb
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def main():
+    torch.manual_seed(0)
+    for (B, Ci, H, W, Co) in LAYERS:
+        x = torch.randn(B, Ci, H, W, device="cuda")
+        off = torch.randn(B, 18, H, W, device="cuda") * 1.5
+        m = torch.sigmoid(torch.randn(B, 9, H, W, device="cuda"))
+        w = torch.randn(Co, Ci, 3, 3, device="cuda") / (3.0 * Ci ** 0.5)
+        go = torch.randn(B, Co, H, W, device="cuda")
+        a = run(x, off, m, w, go, True)
+        a2 = run(x, off, m, w, go, True)
+        r = run(x, off, m, w, go, False)
+        torch.cuda.synchronize()
+        errs = []
+        for name, u, v in zip(("dx", "doff", "dmask", "dw", "db"), a, r):
+            errs.append("%s %.2e/%.1f" % (name, (u - v).abs().max().item(), v.abs().max().item()))
+        det = [bool((u == v).all().item()) for u, v in zip(a, a2)]
+        t_tc = timeit(lambda: run(x, off, m, w, go, True))
+        t_fp = timeit(lambda: run(x, off, m, w, go, False), 3)
+        print("B%d %d@%dx%d->%d  tc %.3f ms  fp32 %.3f ms | %s | bit-identical dx,doff,dmask,dw,db: %s"
+              % (B, Ci, H, W, Co, t_tc, t_fp, "  ".join(errs), det), flush=True)
+
+
+if __name__ == "__main__":
+    main()
