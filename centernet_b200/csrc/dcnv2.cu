@@ -500,6 +500,7 @@ int dcn_forward_tc(const float *input, const float *offset, const float *mask, c
                    const float *bias, float *output, int b, int cin, int h, int w, int cout, int kh, int kw, int sh,
                    int sw, int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream);
 size_t dcn_tc_bwd_workspace_bytes(int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int ph, int dh, int dg);
+extern std::atomic<int> g_dcn_deterministic;
 int dcn_backward_data_tc(const float *input, const float *offset, const float *mask, const float *weight,
                          const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask, int b,
                          int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
@@ -523,6 +524,9 @@ size_t cnb_dcnv2_workspace_bytes(int b, int cin, int cout, int h, int w, int kh,
     return 0;
   return dcn_tc_workspace_bytes(b, cin, h, w, cout, kh, kw, stride, pad, dil, dg);
 }
+
+void cnb_dcnv2_set_deterministic(int on) { g_dcn_deterministic.store(on ? 1 : 0, std::memory_order_relaxed); }
+int cnb_dcnv2_get_deterministic(void) { return g_dcn_deterministic.load(std::memory_order_relaxed); }
 
 size_t cnb_dcnv2_backward_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw, int stride, int pad,
                                           int dil, int dg) {

@@ -17,6 +17,7 @@
 // k_dcn_bwd_weight_tc rebuilds the masked column tile in shared memory exactly as the forward sampler does
 // (never in HBM), keeps a [128 rows = 4 chunks x 32 ch] x Cout accumulator in TMEM over its whole pixel range and
 // writes one partial per CTA; k_dcn_bwd_wreduce adds the partials in a fixed order (deterministic).
+#include <stdlib.h>
 #include "dcnv2_tc.cuh"
 
 namespace cnb {
@@ -226,14 +227,23 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b) {
   return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
 }
 
-// Geometry of one (tap, pixel): fractional parts, mask and (hl*W + wl + W + 1) << 6 | flags
-// (bit 0-3: corner in range, 4: sampling point inside (-1,H)x(-1,W), 5: pixel inside the output map).
+// Geometry of one (tap, pixel): fractional parts, mask and (hl*W + wl + W + 1) << 7 | flags
+// (bit 0-3: corner in range, 4: sampling point inside (-1,H)x(-1,W), 5: pixel inside the output map,
+//  6: "near" -- the top-left corner lies within [-GX_RD, GX_RD + 1] of the pixel's own input position, so the
+//  sample's dX contribution is collected by the deterministic gather (k_dcn_bwd_dx_gather) instead of scattered).
+constexpr int GX_RD = 2;                       // offsets of magnitude < 2 pixels are always near
+constexpr int GX_WIN = 2 * GX_RD + 3;          // candidate output rows / columns per input position
+constexpr int GX_TH = 8, GX_TW = 16;           // input positions per CTA
+constexpr int GX_WH = GX_TH + GX_WIN - 1, GX_WW = GX_TW + GX_WIN - 1;
+constexpr int GX_NC = GX_WIN * GX_WIN * TC_NT; // candidates per position (441)
+constexpr int GX_ROUNDS = (GX_NC + 31) / 32;
 struct __align__(16) BwdMetaTc {
   float lh, lw, m;
   int packed;
 };
 __device__ __forceinline__ BwdMetaTc bwd_meta(const DcnShapeTc &s, const float *__restrict__ off_img,
-                                              const float *__restrict__ mask_img, int gi, int tap, int ho, int wo) {
+                                              const float *__restrict__ mask_img, int gi, int tap, int ho, int wo,
+                                              bool gather = false) {
   const int KT = s.kh * s.kw;
   const long long HWo = (long long)s.Ho * s.Wo;
   BwdMetaTc mt;
@@ -260,8 +270,10 @@ __device__ __forceinline__ BwdMetaTc bwd_meta(const DcnShapeTc &s, const float *
       if (hl + 1 <= s.H - 1 && wl >= 0) flags |= 4;
       if (hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1) flags |= 8;
       base = hl * s.W + wl + s.W + 1;
+      const int dh_ = hl - (ho * s.sh - s.ph), dw_ = wl - (wo * s.sw - s.pw);
+      if (gather && dh_ >= -GX_RD && dh_ <= GX_RD + 1 && dw_ >= -GX_RD && dw_ <= GX_RD + 1) flags |= 64;
     }
-    mt.packed = (base << 6) | flags;
+    mt.packed = (base << 7) | flags;
   }
   return mt;
 }
@@ -270,10 +282,14 @@ __device__ __forceinline__ BwdMetaTc bwd_meta(const DcnShapeTc &s, const float *
 // points into shared memory (every point computed once), then each warp walks (tap, 4 pixels) items with
 // lane = (pixel j, 4-channel quad c4): 16-byte loads of the dcol line and of the four corner lines, next channel
 // block in flight while the current one is reduced.
-__global__ void __launch_bounds__(256, 3)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_dcn_bwd_offmask(const float *__restrict__ xt, const float *__restrict__ offset, const float *__restrict__ mask,
                   const float *__restrict__ dcol, float *__restrict__ dxt, float *__restrict__ goff,
-                  float *__restrict__ gmask, const DcnShapeTc s, const BwdGeom g, const int b_first) {
+                  float *__restrict__ gmask, float *__restrict__ gx_far, const DcnShapeTc s, const BwdGeom g,
+                  const int b_first) {
+  // dxt != NULL: every sample is scattered into the channels-last dX (16-byte reductions);
+  // gx_far != NULL: near samples are left to k_dcn_bwd_dx_gather, far ones go to the NCHW gradient with scalar atomics
   __shared__ BwdMetaTc meta[TC_NT * TC_TP];
   const int KT = s.kh * s.kw;
   const long long HWo = (long long)s.Ho * s.Wo, HW = (long long)s.H * s.W;
@@ -288,48 +304,50 @@ k_dcn_bwd_offmask(const float *__restrict__ xt, const float *__restrict__ offset
   const float *x_img = xt + (long long)b * HW * Cp + c4 * 4;
   float *dx_img = dxt ? dxt + (long long)b * HW * Cp + c4 * 4 : nullptr;
   const float *dc_img = dcol + (long long)bl * HWo * g.Qp * TC_CB + c4 * 4;
+  float *gmask_img = gmask ? gmask + (long long)b * s.mask_bs : nullptr;
+  float *goff_img = goff ? goff + (long long)b * s.off_bs : nullptr;
   const int xs1 = Cp, xs2 = s.W * Cp, xs3 = (s.W + 1) * Cp;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  struct Lines { float4 d, x1, x2, x3, x4; };
   for (int gi = 0; gi < s.dg; ++gi) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < KT * TC_TP; idx += 256) {
       const int tap = idx >> 7, pp = idx & (TC_TP - 1);
-      meta[idx] = bwd_meta(s, off_img, mask_img, gi, tap, ty0 + (pp >> tws), tx0 + (pp & (s.tw - 1)));
+      meta[idx] = bwd_meta(s, off_img, mask_img, gi, tap, ty0 + (pp >> tws), tx0 + (pp & (s.tw - 1)), gx_far != nullptr);
     }
     __syncthreads();
+    const int cb0 = gi * s.cbs_pg;
     for (int tap = 0; tap < KT; ++tap) {
 #pragma unroll 1
       for (int pq = warp; pq < TC_TP / 4; pq += 8) {
         const int pp = pq * 4 + j;
         const BwdMetaTc mt = meta[tap * TC_TP + pp];
-        const int flags = mt.packed & 63;
+        const int flags = mt.packed & 127;
         float am = 0.f, ah = 0.f, aw = 0.f;
-        const long long p = (long long)(ty0 + (pp >> tws)) * s.Wo + tx0 + (pp & (s.tw - 1));
+        const int p = (ty0 + (pp >> tws)) * s.Wo + tx0 + (pp & (s.tw - 1));   // 32-bit offsets within one image (host-checked)
         if (flags & 16) {
-          const int base = (mt.packed >> 6) - (s.W + 1);
+          const int base = (mt.packed >> 7) - (s.W + 1);
           const bool f1 = flags & 1, f2 = flags & 2, f3 = flags & 4, f4 = flags & 8;
           const float lh = mt.lh, lw = mt.lw, hh = 1.f - lh, hw = 1.f - lw, m = mt.m;
           const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-          const float *dc = dc_img + (p * g.Qp + (long long)gi * s.cbs_pg * TC_NT + tap) * TC_CB;
-          const long long xo = (long long)base * Cp + gi * s.cbs_pg * TC_CB;
-          const float *xp = x_img + xo;
-          auto load = [&](int cbi) {
-            Lines L;
-            L.d = __ldg(reinterpret_cast<const float4 *>(dc + cbi * (TC_NT * TC_CB)));
-            const float *xq = xp + cbi * TC_CB;
-            L.x1 = f1 ? __ldg(reinterpret_cast<const float4 *>(xq)) : z4;
-            L.x2 = f2 ? __ldg(reinterpret_cast<const float4 *>(xq + xs1)) : z4;
-            L.x3 = f3 ? __ldg(reinterpret_cast<const float4 *>(xq + xs2)) : z4;
-            L.x4 = f4 ? __ldg(reinterpret_cast<const float4 *>(xq + xs3)) : z4;
-            return L;
-          };
-          Lines cur = load(0);
+          int dco = (p * g.Qp + cb0 * TC_NT + tap) * TC_CB;
+          int xo = base * Cp + cb0 * TC_CB;
+          float4 d = __ldg(reinterpret_cast<const float4 *>(dc_img + dco));
+          float4 x1 = f1 ? __ldg(reinterpret_cast<const float4 *>(x_img + xo)) : z4;
+          float4 x2 = f2 ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs1))) : z4;
+          float4 x3 = f3 ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs2))) : z4;
+          float4 x4 = f4 ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs3))) : z4;
           for (int cbi = 0; cbi < s.cbs_pg; ++cbi) {
-            Lines nxt = cur;
-            if (cbi + 1 < s.cbs_pg) nxt = load(cbi + 1);
-            const float4 d = cur.d, x1 = cur.x1, x2 = cur.x2, x3 = cur.x3, x4 = cur.x4;
+            // next channel block in flight while this one is reduced
+            float4 nd = z4, n1 = z4, n2 = z4, n3 = z4, n4 = z4;
+            if (cbi + 1 < s.cbs_pg) {
+              nd = __ldg(reinterpret_cast<const float4 *>(dc_img + (dco + TC_NT * TC_CB)));
+              const int xn = xo + TC_CB;
+              if (f1) n1 = __ldg(reinterpret_cast<const float4 *>(x_img + xn));
+              if (f2) n2 = __ldg(reinterpret_cast<const float4 *>(x_img + (xn + xs1)));
+              if (f3) n3 = __ldg(reinterpret_cast<const float4 *>(x_img + (xn + xs2)));
+              if (f4) n4 = __ldg(reinterpret_cast<const float4 *>(x_img + (xn + xs3)));
+            }
             // dMask (:297): dcol * unmasked bilinear sample
             float4 v;
             v.x = w1 * x1.x + w2 * x2.x + w3 * x3.x + w4 * x4.x;
@@ -352,13 +370,27 @@ k_dcn_bwd_offmask(const float *__restrict__ xt, const float *__restrict__ offset
             aw += dot4(dm, gw);
             // dX (:182-239): the four corners receive dcol * mask * corner weight
             if (dx_img) {
-              float *gx = dx_img + xo + cbi * TC_CB;
-              if (f1 && w1 != 0.f) red_add_v4(gx, dm.x * w1, dm.y * w1, dm.z * w1, dm.w * w1);
-              if (f2 && w2 != 0.f) red_add_v4(gx + xs1, dm.x * w2, dm.y * w2, dm.z * w2, dm.w * w2);
-              if (f3 && w3 != 0.f) red_add_v4(gx + xs2, dm.x * w3, dm.y * w3, dm.z * w3, dm.w * w3);
-              if (f4 && w4 != 0.f) red_add_v4(gx + xs3, dm.x * w4, dm.y * w4, dm.z * w4, dm.w * w4);
+              if (f1 && w1 != 0.f) red_add_v4(dx_img + xo, dm.x * w1, dm.y * w1, dm.z * w1, dm.w * w1);
+              if (f2 && w2 != 0.f) red_add_v4(dx_img + (xo + xs1), dm.x * w2, dm.y * w2, dm.z * w2, dm.w * w2);
+              if (f3 && w3 != 0.f) red_add_v4(dx_img + (xo + xs2), dm.x * w3, dm.y * w3, dm.z * w3, dm.w * w3);
+              if (f4 && w4 != 0.f) red_add_v4(dx_img + (xo + xs3), dm.x * w4, dm.y * w4, dm.z * w4, dm.w * w4);
+            } else if (gx_far && !(flags & 64)) {
+              const int cw = cbi * TC_CB + c4 * 4, cpg = s.Cin / s.dg;     // channel within the group (pad slots skipped)
+              float *gp = gx_far + ((long long)b * s.Cin + gi * cpg + cw) * HW + base;
+              const float dv[4] = {dm.x, dm.y, dm.z, dm.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (cw + i >= cpg) break;
+                float *q = gp + (long long)i * HW;
+                if (f1 && w1 != 0.f) atomicAdd(q, dv[i] * w1);
+                if (f2 && w2 != 0.f) atomicAdd(q + 1, dv[i] * w2);
+                if (f3 && w3 != 0.f) atomicAdd(q + s.W, dv[i] * w3);
+                if (f4 && w4 != 0.f) atomicAdd(q + s.W + 1, dv[i] * w4);
+              }
             }
-            cur = nxt;
+            d = nd; x1 = n1; x2 = n2; x3 = n3; x4 = n4;
+            dco += TC_NT * TC_CB;
+            xo += TC_CB;
           }
         }
         // fixed-order reduction over the 8 channel quads of a pixel
@@ -371,14 +403,137 @@ k_dcn_bwd_offmask(const float *__restrict__ xt, const float *__restrict__ offset
         // the gradients arrive zero-filled (dcn_v2_func.py:44-48) and every (tap, pixel) has exactly one writer:
         // a plain store is the accumulation
         if ((flags & 32) && c4 == 0) {
-          if (gmask) gmask[(((long long)b * s.dg + gi) * KT + tap) * HWo + p] = am;
-          if (goff) {
-            float *gp = goff + (((long long)b * s.dg + gi) * 2 * KT + 2 * tap) * HWo + p;
-            gp[0] = ah;
-            gp[HWo] = aw;
+          const int go = (gi * KT + tap) * (int)HWo + p;
+          if (gmask_img) gmask_img[go] = am;
+          if (goff_img) {
+            goff_img[2 * go - p] = ah;                 // channel 2 * (gi*KT + tap)
+            goff_img[2 * go - p + (int)HWo] = aw;
           }
         }
       }
+    }
+  }
+}
+
+// Deterministic dX for the near samples.  CTA = 8 x 16 input positions of one image; it lays the geometry of every
+// output pixel whose near samples can land in the tile (14 x 22 pixels x 9 taps) into shared memory, then one warp per
+// position walks the position's 441 candidates (tap, row, column) 32 at a time in a FIXED order: a lane tests whether
+// one corner of its candidate is this position; the hits are taken in lane order and every lane (= channel) adds
+// weight * dcol of the hit.  No atomics: two runs give the same bits.  The tile is transposed through shared memory
+// and added to the NCHW gradient (which already holds the far samples' scatter).
+template <int NCB>
+__global__ void __launch_bounds__(256)
+k_dcn_bwd_dx_gather(const float *__restrict__ offset, const float *__restrict__ mask, const float *__restrict__ dcol,
+                    float *__restrict__ gx, const DcnShapeTc s, const BwdGeom g, const int b_first, const int ptx,
+                    const int pty) {
+  extern __shared__ __align__(16) unsigned char gx_smem[];
+  BwdMetaTc *meta = reinterpret_cast<BwdMetaTc *>(gx_smem);                                  // [9][14][22]
+  float(*tile)[GX_TH * GX_TW + 1] =
+      reinterpret_cast<float(*)[GX_TH * GX_TW + 1]>(gx_smem + sizeof(BwdMetaTc) * TC_NT * GX_WH * GX_WW);   // [NCB*32][129]
+  const int KT = s.kh * s.kw, cpg = s.Cin / s.dg;
+  const long long HWo = (long long)s.Ho * s.Wo, HW = (long long)s.H * s.W;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tix = blockIdx.x % ptx, tiy = (blockIdx.x / ptx) % pty, bl = blockIdx.x / (ptx * pty);
+  const int b = b_first + bl;
+  const int y0 = tiy * GX_TH, x0 = tix * GX_TW;
+  const int ho0 = y0 + s.ph - GX_RD - 2, wo0 = x0 + s.pw - GX_RD - 2;     // first output row / column of the window (stride 1)
+  const float *off_img = offset + (long long)b * s.off_bs, *mask_img = mask + (long long)b * s.mask_bs;
+  const float *dc_img = dcol + (long long)bl * HWo * g.Qp * TC_CB + lane;
+
+  // candidate (tap, r, c) of this lane in every round: its index into the geometry window and into dcol
+  int moff[GX_ROUNDS], doff[GX_ROUNDS];
+#pragma unroll
+  for (int rnd = 0; rnd < GX_ROUNDS; ++rnd) {
+    const int cand = rnd * 32 + lane;
+    const int tap = cand / (GX_WIN * GX_WIN), rc = cand - tap * (GX_WIN * GX_WIN);
+    const int r = rc / GX_WIN, c = rc - r * GX_WIN;
+    moff[rnd] = cand < GX_NC ? (tap * GX_WH + r) * GX_WW + c : -1;
+    doff[rnd] = ((r * s.Wo + c) * g.Qp + tap) * TC_CB;
+  }
+
+  for (int gi = 0; gi < s.dg; ++gi) {
+    __syncthreads();
+    for (int idx = tid; idx < TC_NT * GX_WH * GX_WW; idx += 256) {
+      const int tap = idx / (GX_WH * GX_WW), rem = idx - tap * (GX_WH * GX_WW);
+      const int ho = ho0 + rem / GX_WW, wo = wo0 + rem % GX_WW;
+      BwdMetaTc mt;
+      mt.lh = mt.lw = mt.m = 0.f;
+      mt.packed = 0;
+      if (ho >= 0 && wo >= 0 && tap < KT) mt = bwd_meta(s, off_img, mask_img, gi, tap, ho, wo, true);
+      meta[idx] = mt;
+    }
+    __syncthreads();
+    for (int cbg = 0; cbg < s.cbs_pg; cbg += NCB) {
+      const int ncb = min(NCB, s.cbs_pg - cbg);
+      // warp = one row of the position tile
+      for (int px = 0; px < GX_TW; ++px) {
+        const int y = y0 + warp, x = x0 + px;
+        float acc[NCB];
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) acc[cb] = 0.f;
+        if (y < s.H && x < s.W) {
+          const int mbase = warp * GX_WW + px;
+          const int posk = y * s.W + x + s.W + 1;
+          const int dbase = (((ho0 + warp) * s.Wo + wo0 + px) * g.Qp + (gi * s.cbs_pg + cbg) * TC_NT) * TC_CB;
+#pragma unroll
+          for (int rnd = 0; rnd < GX_ROUNDS; ++rnd) {
+            float wgt = 0.f;
+            bool hit = false;
+            if (moff[rnd] >= 0) {
+              const BwdMetaTc e = meta[moff[rnd] + mbase];
+              if (e.packed & 64) {
+                const int diff = posk - (e.packed >> 7);
+                const float hh = 1.f - e.lh, hw = 1.f - e.lw;
+                if (diff == 0) { hit = e.packed & 1; wgt = hh * hw; }
+                else if (diff == 1) { hit = e.packed & 2; wgt = hh * e.lw; }
+                else if (diff == s.W) { hit = e.packed & 4; wgt = e.lh * hw; }
+                else if (diff == s.W + 1) { hit = e.packed & 8; wgt = e.lh * e.lw; }
+                wgt *= e.m;
+              }
+            }
+            unsigned hits = __ballot_sync(0xffffffffu, hit);
+            while (hits) {        // warp-uniform: up to 4 hits per pass, their loads in flight together, added in lane order
+              float w[4], v[4][NCB];
+              int o[4], n = 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (hits) {
+                  const int src = __ffs(hits) - 1;
+                  hits &= hits - 1;
+                  w[k] = __shfl_sync(0xffffffffu, wgt, src);
+                  o[k] = __shfl_sync(0xffffffffu, doff[rnd], src) + dbase;
+                  n = k + 1;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < n) {
+#pragma unroll
+                  for (int cb = 0; cb < NCB; ++cb)
+                    if (cb < ncb) v[k][cb] = __ldg(dc_img + (o[k] + cb * TC_NT * TC_CB));
+                }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < n) {
+#pragma unroll
+                  for (int cb = 0; cb < NCB; ++cb)
+                    if (cb < ncb) acc[cb] = fmaf(w[k], v[k][cb], acc[cb]);
+                }
+            }
+          }
+        }
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) tile[cb * TC_CB + lane][warp * GX_TW + px] = acc[cb];
+      }
+      __syncthreads();
+      // tile[channel][position] -> gx[b][channel][y][x], 16 consecutive x per row
+      for (int i = tid; i < ncb * TC_CB * GX_TH * GX_TW; i += 256) {
+        const int pp = i & (GX_TH * GX_TW - 1), cl = i >> 7;
+        const int cw = cbg * TC_CB + cl;                   // channel within the group
+        const int y = y0 + (pp >> 4), x = x0 + (pp & 15);
+        if (cw < cpg && y < s.H && x < s.W) gx[((long long)b * s.Cin + gi * cpg + cw) * HW + (long long)y * s.W + x] += tile[cl][pp];
+      }
+      __syncthreads();
     }
   }
 }
@@ -412,6 +567,16 @@ __global__ void __launch_bounds__(256) k_dcn_bwd_dx_nchw(const float *__restrict
 // ------------------------------------------------------------------ dW = dY . col^T   (K = pixels)
 constexpr int WG_SAMPLERS = 16;
 constexpr int WG_THREADS = (TC_WARP_S0 + WG_SAMPLERS) * 32;   // warps 0-3 epilogue, 4 MMA, 5 TMA, 6-21 samplers
+constexpr uint32_t WG_SBO = 1040;                             // pitch of the A tile's 8-row groups (bank-conflict-free scalar stores)
+constexpr int WG_A_BYTES = (TC_TP / 8) * WG_SBO;              // 16640 per hi / lo tile
+__device__ __forceinline__ uint64_t wg_desc_a(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((TC_LBO >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((WG_SBO >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 
 struct WgGeom {
   int co_r;          // Cout rounded up to 16 (UMMA N)
@@ -419,7 +584,7 @@ struct WgGeom {
   int n_slices;      // B * spi
   int splits;        // pixel-range splits (CTAs per row group)
   int stages;
-  int stage_bytes;   // 2 * TC_A_BYTES + 2 * co_r * 128
+  int stage_bytes;   // 2 * WG_A_BYTES + 2 * co_r * 128
   unsigned wo_magic; // floor(2^32 / Wo) + 1: p / Wo == umulhi(p, magic) for p < 2^32 / Wo; 0 = divide
 };
 static WgGeom wg_geom(const DcnShapeTc &s, const BwdGeom &g) {
@@ -427,12 +592,12 @@ static WgGeom wg_geom(const DcnShapeTc &s, const BwdGeom &g) {
   w.co_r = (s.Cout + 15) / 16 * 16;
   w.spi = (int)(((long long)s.Ho * s.Wo + TC_K - 1) / TC_K);
   w.n_slices = s.B * w.spi;
-  int splits = (num_sms() + g.RG - 1) / g.RG;
+  int splits = num_sms() / g.RG;          // one CTA per SM at most (a CTA owns ~200 KB of shared memory): no second wave
   if (splits > w.n_slices) splits = w.n_slices;
   if (splits < 1) splits = 1;
   w.splits = splits;
-  w.stage_bytes = 2 * TC_A_BYTES + 2 * w.co_r * TC_K * 4;
-  w.stages = w.stage_bytes <= 65536 ? 3 : 2;
+  w.stage_bytes = 2 * WG_A_BYTES + 2 * w.co_r * TC_K * 4;
+  w.stages = w.stage_bytes <= 66048 ? 3 : 2;
   w.wo_magic = ((unsigned long long)s.Ho * s.Wo * s.Wo < (1ull << 32)) ? (unsigned)((1ull << 32) / (unsigned)s.Wo + 1) : 0u;
   return w;
 }
@@ -486,6 +651,7 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
   extern __shared__ __align__(128) unsigned char tc_smem[];
   __shared__ __align__(8) uint64_t a_full[3], b_full[3], empty[3], tm_full;
   __shared__ uint32_t tmem_base;
+  __shared__ BwdMetaTc wmeta[2][128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rg = blockIdx.x % g.RG, split = blockIdx.x / g.RG;
   const int sl0 = (int)((long long)split * wg.n_slices / wg.splits), sl1 = (int)((long long)(split + 1) * wg.n_slices / wg.splits);
@@ -510,112 +676,91 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
 
   if (warp >= TC_WARP_S0) {
     // =========================================================== samplers: the masked column tile, rows = channels
-    const int sw = warp - TC_WARP_S0;
-    const int j = lane >> 3, c4 = lane & 7;       // gather: lane = (pixel j of 4, channel quad c4): one line per quarter-warp
-    const int rj = lane & 3, rc4 = lane >> 2;     // store:  lane = (channel c4' * 4 + j'): 8 consecutive rows per quarter-warp
-    const bool sel1 = rj & 1, sel2 = rj & 2;
-    // per-task constants (task = sw + 16 it: chunk ql = task / 8, pixel group pg = task % 8)
-    bool t_ok[2];
-    int t_pp[2], t_hb[2], t_wb[2];
-    const float *t_off[2], *t_msk[2], *t_x[2];
+    // Geometry of a slice's 4 taps x 32 pixels is computed once (threads 0..127 of the samplers, one slice ahead,
+    // double-buffered in shared memory); then task = (chunk ql, 4 pixels): lane = (pixel j, channel quad c4) gathers
+    // 4 corners x 16 bytes and stores its 4 channels x 1 pixel as scalars -- the 8-row groups of the A tile are
+    // pitched WG_SBO = 1040 bytes so that the 32 lanes of a store hit 32 different banks.
+    const int sw = warp - TC_WARP_S0, st = tid - TC_WARP_S0 * 32;
+    const int j = lane >> 3, c4 = lane & 7;
+    int t_meta[2], t_xc[2];
     uint32_t t_dst[2];
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const int task = sw + it * WG_SAMPLERS;
+      const int task = sw + it * WG_SAMPLERS;      // chunk ql = task / 8, pixel group pg = task % 8
       const int ql = task >> 3, pg = task & 7;
       const int q = rg * 4 + ql;
-      const int bi = q / TC_NT, tap = q - bi * TC_NT;
-      const int gi = bi / s.cbs_pg;
-      const int ki = tap / s.kw, kj = tap - ki * s.kw;
-      t_ok[it] = q < g.Q && tap < KT;
-      t_pp[it] = pg * 4 + j;
-      t_hb[it] = ki * s.dh - s.ph;
-      t_wb[it] = kj * s.dw - s.pw;
-      t_off[it] = offset + ((long long)gi * 2 * KT + 2 * tap) * HWo;
-      t_msk[it] = mask + ((long long)gi * KT + tap) * HWo;
-      t_x[it] = xt + bi * TC_CB + c4 * 4;
-      t_dst[it] = tc_tile_off(ql * 32 + rc4 * 4 + rj, pg * 4);
+      const int bi = q < g.Q ? q / TC_NT : 0;
+      t_meta[it] = ql * 32 + pg * 4 + j;
+      t_xc[it] = bi * TC_CB + c4 * 4;
+      const int row = ql * 32 + c4 * 4;            // + i (i < 4 stays inside one 8-row group)
+      t_dst[it] = (uint32_t)(row >> 3) * WG_SBO + (uint32_t)pg * TC_LBO + (uint32_t)(row & 7) * 16u + (uint32_t)j * 4u;
     }
-    const int HWo_i = (int)HWo;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int stage = 0, ph = 0;
-    int b = sl0 / wg.spi, sll = sl0 - b * wg.spi;      // image and slice within the image
-    // offsets / mask of the first slice; afterwards they are fetched one slice ahead
-    float pdy[2], pdx[2], pm[2];
-    auto fetch = [&](int bb, int sl_local) {
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int p = sl_local * TC_K + t_pp[it];
-        pdy[it] = pdx[it] = pm[it] = 0.f;
-        if (t_ok[it] && p < HWo_i) {
-          pdy[it] = __ldg(t_off[it] + (long long)bb * s.off_bs + p);
-          pdx[it] = __ldg(t_off[it] + (long long)bb * s.off_bs + HWo + p);
-          pm[it] = __ldg(t_msk[it] + (long long)bb * s.mask_bs + p);
-        }
-      }
+    // the geometry entry this thread produces (st < 128): chunk st / 32, pixel st % 32 of the slice
+    const int m_q = rg * 4 + (st >> 5);
+    const int m_bi = m_q / TC_NT, m_tap = (st < 128 && m_q < g.Q) ? m_q - m_bi * TC_NT : TC_NT;   // TC_NT = "no such tap"
+    const int m_gi = m_bi / s.cbs_pg;
+    auto geometry = [&](int bb, int sl_local) {
+      const int p = sl_local * TC_K + (st & 31);
+      const int ho = wg.wo_magic ? (int)__umulhi((unsigned)p, wg.wo_magic) : p / s.Wo;
+      return bwd_meta(s, offset + (long long)bb * s.off_bs, mask + (long long)bb * s.mask_bs, m_gi, m_tap, ho, p - ho * s.Wo);
     };
-    if (sl0 < sl1) fetch(b, sll);
+    const int xs1 = Cp, xs2 = s.W * Cp, xs3 = (s.W + 1) * Cp;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int stage = 0, ph = 0, par = 0;
+    int b = sl0 / wg.spi, sll = sl0 - b * wg.spi;      // image and slice within the image
+    if (st < 128 && sl0 < sl1) wmeta[0][st] = geometry(b, sll);
+    named_bar_sync(1, WG_SAMPLERS * 32);
     for (int sl = sl0; sl < sl1; ++sl) {
-      float dy[2], dx[2], m[2];
-#pragma unroll
-      for (int it = 0; it < 2; ++it) { dy[it] = pdy[it]; dx[it] = pdx[it]; m[it] = pm[it]; }
       int nb_ = b, nsl = sll + 1;
       if (nsl == wg.spi) { nsl = 0; ++nb_; }
-      if (sl + 1 < sl1) fetch(nb_, nsl);
+      BwdMetaTc nmeta;
+      if (st < 128 && sl + 1 < sl1) nmeta = geometry(nb_, nsl);       // its loads fly while this slice is sampled
+      const float *x_img = xt + (long long)b * HW * Cp;
+      // both tasks' eight corner loads are issued before anything is used; a corner that is out of range (or a sample
+      // that is outside altogether: all four flags clear, weights zero) is simply not loaded
+      BwdMetaTc mt[2];
+      float4 xc[2][4];
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        mt[it] = wmeta[par][t_meta[it]];
+        const int flags = mt[it].packed;
+        const int xo = ((flags >> 7) - (s.W + 1)) * Cp + t_xc[it];
+        xc[it][0] = (flags & 1) ? __ldg(reinterpret_cast<const float4 *>(x_img + xo)) : z4;
+        xc[it][1] = (flags & 2) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs1))) : z4;
+        xc[it][2] = (flags & 4) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs2))) : z4;
+        xc[it][3] = (flags & 8) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs3))) : z4;
+      }
       float4 val[2];
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
-        const int p = sll * TC_K + t_pp[it];
-        float4 v = z4;
-        if (t_ok[it] && p < HWo_i) {
-          const int ho = wg.wo_magic ? (int)__umulhi((unsigned)p, wg.wo_magic) : p / s.Wo;
-          const int wo = p - ho * s.Wo;
-          const float h_im = (float)(ho * s.sh + t_hb[it]) + dy[it];
-          const float w_im = (float)(wo * s.sw + t_wb[it]) + dx[it];
-          if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {   // dcn_v2_im2col_cuda.cu:165
-            const float hf = floorf(h_im), wf = floorf(w_im);
-            const int hl = (int)hf, wl = (int)wf;
-            const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-            const float *xb = t_x[it] + ((long long)b * HW + (long long)hl * s.W + wl) * Cp;
-            const bool f1 = hl >= 0 && wl >= 0, f2 = hl >= 0 && wl + 1 <= s.W - 1;
-            const bool f3 = hl + 1 <= s.H - 1 && wl >= 0, f4 = hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1;
-            const float4 x1 = f1 ? __ldg(reinterpret_cast<const float4 *>(xb)) : z4;
-            const float4 x2 = f2 ? __ldg(reinterpret_cast<const float4 *>(xb + Cp)) : z4;
-            const float4 x3 = f3 ? __ldg(reinterpret_cast<const float4 *>(xb + (long long)s.W * Cp)) : z4;
-            const float4 x4 = f4 ? __ldg(reinterpret_cast<const float4 *>(xb + (long long)(s.W + 1) * Cp)) : z4;
-            const float mm = m[it];
-            const float w1 = hh * hw * mm, w2 = hh * lw * mm, w3 = lh * hw * mm, w4 = lh * lw * mm;   // as the forward sampler
-            v.x = fmaf(w4, x4.x, fmaf(w3, x3.x, fmaf(w2, x2.x, w1 * x1.x)));
-            v.y = fmaf(w4, x4.y, fmaf(w3, x3.y, fmaf(w2, x2.y, w1 * x1.y)));
-            v.z = fmaf(w4, x4.z, fmaf(w3, x3.z, fmaf(w2, x2.z, w1 * x1.z)));
-            v.w = fmaf(w4, x4.w, fmaf(w3, x3.w, fmaf(w2, x2.w, w1 * x1.w)));
-          }
-        }
+        const float lh = mt[it].lh, lw = mt[it].lw, mm = mt[it].m, hh = 1.f - lh, hw = 1.f - lw;
+        const float w1 = hh * hw * mm, w2 = hh * lw * mm, w3 = lh * hw * mm, w4 = lh * lw * mm;   // as the forward sampler
+        const float4 x1 = xc[it][0], x2 = xc[it][1], x3 = xc[it][2], x4 = xc[it][3];
+        float4 v;
+        v.x = fmaf(w4, x4.x, fmaf(w3, x3.x, fmaf(w2, x2.x, w1 * x1.x)));
+        v.y = fmaf(w4, x4.y, fmaf(w3, x3.y, fmaf(w2, x2.y, w1 * x1.y)));
+        v.z = fmaf(w4, x4.z, fmaf(w3, x3.z, fmaf(w2, x2.z, w1 * x1.z)));
+        v.w = fmaf(w4, x4.w, fmaf(w3, x3.w, fmaf(w2, x2.w, w1 * x1.w)));
         val[it] = v;
       }
       mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
       unsigned char *a_hi = tc_smem + (size_t)stage * wg.stage_bytes;
-      unsigned char *a_lo = a_hi + TC_A_BYTES;
+      unsigned char *a_lo = a_hi + WG_A_BYTES;
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
-        // 4x4 transpose across the lanes of one channel quad: this lane ends up with channel rc4*4+rj of pixels 0..3
-        float u[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int src = i * 8 + rc4;
-          const float t0 = __shfl_sync(0xffffffffu, val[it].x, src), t1 = __shfl_sync(0xffffffffu, val[it].y, src);
-          const float t2 = __shfl_sync(0xffffffffu, val[it].z, src), t3 = __shfl_sync(0xffffffffu, val[it].w, src);
-          const float lo01 = sel1 ? t1 : t0, hi23 = sel1 ? t3 : t2;
-          u[i] = sel2 ? hi23 : lo01;
-        }
-        const float4 h4 = make_float4(tf32_hi(u[0]), tf32_hi(u[1]), tf32_hi(u[2]), tf32_hi(u[3]));
-        *reinterpret_cast<float4 *>(a_hi + t_dst[it]) = h4;
-        *reinterpret_cast<float4 *>(a_lo + t_dst[it]) = make_float4(u[0] - h4.x, u[1] - h4.y, u[2] - h4.z, u[3] - h4.w);
+        const float4 v = val[it];
+        const float4 h4 = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        float *dh = reinterpret_cast<float *>(a_hi + t_dst[it]), *dl = reinterpret_cast<float *>(a_lo + t_dst[it]);
+        dh[0] = h4.x; dh[4] = h4.y; dh[8] = h4.z; dh[12] = h4.w;                          // rows c4*4 + 0..3: 16 bytes apart
+        dl[0] = v.x - h4.x; dl[4] = v.y - h4.y; dl[8] = v.z - h4.z; dl[12] = v.w - h4.w;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_tc(&a_full[stage]);
       if (++stage == wg.stages) { stage = 0; ph ^= 1; }
+      if (st < 128 && sl + 1 < sl1) wmeta[par ^ 1][st] = nmeta;
+      named_bar_sync(1, WG_SAMPLERS * 32);
+      par ^= 1;
       b = nb_;
       sll = nsl;
     }
@@ -624,7 +769,7 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
       int stage = 0, ph = 0;
       for (int sl = sl0; sl < sl1; ++sl) {
         mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
-        unsigned char *dst = tc_smem + (size_t)stage * wg.stage_bytes + 2 * TC_A_BYTES;
+        unsigned char *dst = tc_smem + (size_t)stage * wg.stage_bytes + 2 * WG_A_BYTES;
         const unsigned char *src = reinterpret_cast<const unsigned char *>(gyk) + (size_t)sl * 2 * b_bytes;
         mbar_expect_tx(&b_full[stage], 2u * (uint32_t)b_bytes);
         for (uint32_t off = 0; off < 2u * (uint32_t)b_bytes; off += 2048u) bulk_g2s(dst + off, src + off, 2048u, &b_full[stage]);
@@ -639,12 +784,12 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
         mbar_wait(&a_full[stage], (uint32_t)ph);
         mbar_wait(&b_full[stage], (uint32_t)ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ah = smem_u32(tc_smem + (size_t)stage * wg.stage_bytes), al = ah + TC_A_BYTES;
-        const uint32_t bh = al + TC_A_BYTES, bl = bh + (uint32_t)b_bytes;
+        const uint32_t ah = smem_u32(tc_smem + (size_t)stage * wg.stage_bytes), al = ah + WG_A_BYTES;
+        const uint32_t bh = al + WG_A_BYTES, bl = bh + (uint32_t)b_bytes;
 #pragma unroll
         for (int k8 = 0; k8 < TC_K / 8; ++k8) {
           const uint32_t koff = (uint32_t)k8 * 2u * TC_LBO;
-          const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
+          const uint64_t dah = wg_desc_a(ah + koff), dal = wg_desc_a(al + koff);
           const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
           umma_tf32(tm, dal, dbh, idesc, (sl > sl0 || k8 > 0) ? 1u : 0u);
           umma_tf32(tm, dah, dbl, idesc, 1u);
@@ -704,6 +849,7 @@ __global__ void __launch_bounds__(256) k_dcn_bwd_wreduce(const float *__restrict
 }
 
 // ------------------------------------------------------------------ host
+std::atomic<int> g_dcn_deterministic{0};
 static size_t bw_xt_bytes(const DcnShapeTc &s) { return align_up((size_t)s.B * s.H * s.W * s.nb * TC_CB * 4, 256); }
 static size_t bw_wtt_bytes(const BwdGeom &g) { return align_up((size_t)g.RG * g.KS * BW_TILE_FLOATS * 4, 256); }
 static size_t bw_gyt_bytes_per_image(const BwdGeom &g) { return (size_t)g.tiles * g.KS * BW_TILE_FLOATS * 4; }
@@ -731,6 +877,11 @@ size_t dcn_tc_bwd_workspace_bytes(int b, int cin, int h, int w, int cout, int kh
   DcnShapeTc s;
   fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sh, ph, ph, dh, dh, dg);
   const BwdGeom g = bwd_geom(s);
+  // the kernels index within one image with 32 bits (and pack hl*W+wl into 24): larger images use the fp32 path
+  const unsigned long long lim = 1ull << 31;
+  if ((unsigned long long)(h + 2) * (w + 2) >= (1ull << 24) || (unsigned long long)(h + 2) * (w + 2) * s.nb * TC_CB >= lim ||
+      (unsigned long long)s.Ho * s.Wo * g.Qp * TC_CB >= lim || (unsigned long long)s.Ho * s.Wo * dg * 2 * kh * kw >= lim)
+    return 0;
   const WgGeom wg = wg_geom(s, g);
   const int bc = bw_batch_chunk(s, g);
   const size_t data = align_up((size_t)bc * bw_gyt_bytes_per_image(g), 256) + (size_t)bc * bw_dcol_bytes_per_image(s, g);
@@ -758,7 +909,11 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
   int rc = CNB_OK;
   if (!xt_ready) rc = dcn_to_channels_last(input, xt, s, stream);
   if (rc != CNB_OK) return rc;
-  if (grad_input) CNB_CUDA(cudaMemsetAsync(dxt, 0, (size_t)b * HW * s.nb * TC_CB * 4, stream));
+  // default: every sample is scattered into a channels-last dX (16-byte vector reductions) and added to grad_input at
+  // the end; deterministic mode (cnb_dcnv2_set_deterministic, stride 1): near samples by the gather, the rest by atomics
+  // straight into grad_input
+  const bool gather = grad_input && sh == 1 && sw == 1 && w >= 2 && g_dcn_deterministic.load(std::memory_order_relaxed) != 0;
+  if (grad_input && !gather) CNB_CUDA(cudaMemsetAsync(dxt, 0, (size_t)b * HW * s.nb * TC_CB * 4, stream));
   k_bwd_prep_w<<<g.RG * g.KS, 256, 0, stream>>>(weight, s, g, wtt);
   CNB_CHECK_LAUNCH("cnb_dcnv2_backward weight tiles");
   count_launch();
@@ -779,12 +934,29 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
     const int grid = n_items < num_sms() ? n_items : num_sms();
     k_dcn_bwd_dcol_tc<<<grid, BW_THREADS, smem, stream>>>(gyt, wtt, dcol, s, g, n_items);
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward column gradient (tcgen05)");
-    k_dcn_bwd_offmask<<<nbimg * g.tiles, 256, 0, stream>>>(xt, offset, mask, dcol, grad_input ? dxt : nullptr, grad_offset,
-                                                           grad_mask, s, g, b0);
+    k_dcn_bwd_offmask<3><<<nbimg * g.tiles, 256, 0, stream>>>(xt, offset, mask, dcol, (grad_input && !gather) ? dxt : nullptr,
+                                                              grad_offset, grad_mask, gather ? grad_input : nullptr, s, g, b0);
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward offset/mask gradient");
     count_launch(3);
+    if (gather) {
+      const int ptx = (w + GX_TW - 1) / GX_TW, pty = (h + GX_TH - 1) / GX_TH;
+      const int ncb = s.cbs_pg >= 2 ? 2 : 1;
+      const size_t gsm = sizeof(BwdMetaTc) * TC_NT * GX_WH * GX_WW + (size_t)ncb * TC_CB * (GX_TH * GX_TW + 1) * 4;
+      static thread_local int gdev_done = -1;
+      if (gdev_done != dev) {
+        CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_dx_gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_dx_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        gdev_done = dev;
+      }
+      if (ncb == 2)
+        k_dcn_bwd_dx_gather<2><<<nbimg * ptx * pty, 256, gsm, stream>>>(offset, mask, dcol, grad_input, s, g, b0, ptx, pty);
+      else
+        k_dcn_bwd_dx_gather<1><<<nbimg * ptx * pty, 256, gsm, stream>>>(offset, mask, dcol, grad_input, s, g, b0, ptx, pty);
+      CNB_CHECK_LAUNCH("cnb_dcnv2_backward input gradient (gather)");
+      count_launch();
+    }
   }
-  if (grad_input) {
+  if (grad_input && !gather) {
     dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((cin + 63) / 64), (unsigned)b);
     k_dcn_bwd_dx_nchw<<<tgrid, 256, 0, stream>>>(dxt, grad_input, s);
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward input gradient");
@@ -819,7 +991,7 @@ int dcn_backward_weight_tc(const float *input, const float *offset, const float 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev_done != dev) {
-    CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_weight_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536));
+    CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_weight_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 66048));
     dev_done = dev;
   }
   k_dcn_bwd_weight_tc<<<g.RG * wg.splits, WG_THREADS, smem, stream>>>(xt, offset, mask, gyk, wpart, s, g, wg);

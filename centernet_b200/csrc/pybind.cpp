@@ -188,6 +188,8 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("dcnv2_workspace_bytes", &cnb_dcnv2_workspace_bytes);
   m.def("dcnv2_backward_workspace_bytes", &cnb_dcnv2_backward_workspace_bytes);
+  m.def("dcnv2_set_deterministic", &cnb_dcnv2_set_deterministic);
+  m.def("dcnv2_get_deterministic", &cnb_dcnv2_get_deterministic);
   m.def("dcnv2_forward", [](P input, P offset, P mask, P weight, P bias, P output, int b, int cin, int h, int w,
                             int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg, P ws,
                             size_t wsb, P stream) {

@@ -16,6 +16,9 @@ from ._lib import C, f32c, ptr, stream_ptr, workspace
 
 # CNB_DCN_FP32=1 selects the fp32 CUDA-core contraction instead of the tcgen05 (3xTF32) one
 _FORCE_FP32 = os.environ.get("CNB_DCN_FP32", "0") == "1"
+# CNB_DCN_DETERMINISTIC=1: bit-identical grad_input (cnb_dcnv2_set_deterministic); also on under
+# torch.use_deterministic_algorithms(True)
+_DETERMINISTIC = os.environ.get("CNB_DCN_DETERMINISTIC", "0") == "1"
 
 
 def _out_hw(h, w, kh, kw, stride, padding, dilation):
@@ -106,6 +109,8 @@ class _DCNv2(Function):
         gmsk = torch.zeros_like(msk)
         gw = torch.zeros_like(w)
         gb = torch.zeros_like(b) if b is not None else None
+        # grad_input by the fixed-order gather when the user asked torch for deterministic algorithms (or CNB_DCN_DETERMINISTIC=1)
+        C.dcnv2_set_deterministic(int(_DETERMINISTIC or torch.are_deterministic_algorithms_enabled()))
         ws, wsb = 0, 0
         if not _FORCE_FP32:
             wsb = C.dcnv2_backward_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding, dilation, dg)

@@ -252,6 +252,14 @@ int cnb_dcnv2_forward_fused(const float *input, int input_channels_last, const f
                             void *workspace, size_t workspace_bytes, void *stream);
 size_t cnb_dcnv2_backward_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
                                           int stride, int pad, int dil, int dg);
+/* grad_offset, grad_mask, grad_weight and grad_bias of the tensor-core backward are bit-identical run to run.
+ * grad_input is by default scattered with (vector) atomics like the reference's col2im
+ * (dcn_v2_im2col_cuda.cu:182-239), i.e. its last bits depend on the order the adds land.  on != 0 selects a
+ * gather instead (stride 1): every input position collects the samples that fall on it in a fixed order, which
+ * makes grad_input bit-identical as well as long as no offset moves a sample more than 2 pixels from its tap
+ * (those few still go through atomics); it costs about one extra forward.  Process-wide, default off. */
+void cnb_dcnv2_set_deterministic(int on);
+int cnb_dcnv2_get_deterministic(void);
 int cnb_dcnv2_backward(const float *input, const float *offset, const float *mask,
                        const float *weight, const float *grad_output,
                        float *grad_input, float *grad_offset, float *grad_mask,

@@ -118,6 +118,35 @@ def test_backward_tensor_core_vs_fp32_path(B, Ci, H, W, Co, dg, stride):
         assert torch.equal(u, v), name + " not bit-identical run to run"
 
 
+@pytest.mark.parametrize("B,Ci,H,W,Co,dg", [(2, 64, 40, 48, 64, 1), (2, 96, 17, 23, 40, 1), (1, 64, 16, 24, 32, 2), (2, 160, 12, 12, 24, 1)])
+def test_backward_deterministic_mode(B, Ci, H, W, Co, dg):
+    """cnb_dcnv2_set_deterministic(1): grad_input through the fixed-order gather.  Offsets within +-1.9 pixels keep every
+    sample in the gather window, so ALL five gradients repeat bit for bit; with free offsets the far samples take the
+    atomic path and the result still matches the fp32 path."""
+    from centernet_b200._lib import C
+    x, off, m, w, _ = [t.cuda() for t in make(B, Ci, H, W, Co, dg, 1, seed=13, off_scale=1.5)]
+    go = torch.randn(B, Co, H, W, generator=torch.Generator().manual_seed(6)).cuda()
+    r = _raw_backward(x, off, m, w, go, 1, dg, False)
+    try:
+        C.dcnv2_set_deterministic(1)
+        assert C.dcnv2_get_deterministic() == 1
+        a = _raw_backward(x, off, m, w, go, 1, dg, True)
+        offc = off.clamp(-1.9, 1.9)
+        d1 = _raw_backward(x, offc, m, w, go, 1, dg, True)
+        d2 = _raw_backward(x, offc, m, w, go, 1, dg, True)
+    finally:
+        C.dcnv2_set_deterministic(0)
+    rc = _raw_backward(x, offc, m, w, go, 1, dg, False)
+    for name, u, v in zip(("input", "offset", "mask", "weight", "bias"), a, r):
+        scale = max(1.0, v.abs().max().item())
+        assert (u - v).abs().max().item() <= 2e-4 * scale, (name, (u - v).abs().max().item(), scale)
+    for name, u, v in zip(("input", "offset", "mask", "weight", "bias"), d1, rc):
+        scale = max(1.0, v.abs().max().item())
+        assert (u - v).abs().max().item() <= 2e-4 * scale, ("clamped", name, (u - v).abs().max().item(), scale)
+    for name, u, v in zip(("input", "offset", "mask", "weight", "bias"), d1, d2):
+        assert torch.equal(u, v), name + " not bit-identical run to run in deterministic mode"
+
+
 def test_dcn_module_and_state_dict_names():
     from centernet_b200.dcn_v2 import DCN
     dcn = DCN(16, 8, kernel_size=(3, 3), stride=1, padding=1, deformable_groups=1).cuda()

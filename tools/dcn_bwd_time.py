@@ -13,7 +13,7 @@ LAYERS = [(16, 64, 128, 128, 64), (16, 128, 64, 64, 128), (16, 256, 32, 32, 256)
           (16, 128, 64, 64, 64), (16, 256, 32, 32, 128)]
 
 
-def run(x, off, m, w, go, tc):
+def run(x, off, m, w, go, tc, want_dx=True):
     B, Ci, H, W = x.shape
     Co = w.shape[0]
     gx = torch.zeros_like(x); goff = torch.zeros_like(off); gm = torch.zeros_like(m)
@@ -22,7 +22,7 @@ def run(x, off, m, w, go, tc):
     if tc:
         wsb = C.dcnv2_backward_workspace_bytes(B, Ci, Co, H, W, 3, 3, 1, 1, 1, 1)
         wsbuf = workspace(wsb, x.device); ws = ptr(wsbuf)
-    C.dcnv2_backward(ptr(x), ptr(off), ptr(m), ptr(w), ptr(go), ptr(gx), ptr(goff), ptr(gm), ptr(gw), ptr(gb),
+    C.dcnv2_backward(ptr(x), ptr(off), ptr(m), ptr(w), ptr(go), ptr(gx) if want_dx else 0, ptr(goff), ptr(gm), ptr(gw), ptr(gb),
                      B, Ci, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, ws, wsb, stream_ptr(x))
     return gx, goff, gm, gw, gb
 
@@ -40,14 +40,30 @@ def timeit(fn, n=10):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, nargs="*", default=None, help="indices into LAYERS (default: all)")
+    ap.add_argument("--quick", action="store_true", help="tensor-core path only, one call per layer (for ncu)")
+    ap.add_argument("--deterministic", action="store_true", help="cnb_dcnv2_set_deterministic(1): dX by the gather")
+    ap.add_argument("--off-scale", type=float, default=1.5)
+    ap.add_argument("--off-clamp", type=float, default=0.0, help="clamp the offsets to +-this (0 = no clamp)")
+    args = ap.parse_args()
     torch.manual_seed(0)
-    for (B, Ci, H, W, Co) in LAYERS:
+    C.dcnv2_set_deterministic(int(args.deterministic))
+    for li, (B, Ci, H, W, Co) in enumerate(LAYERS):
+        if args.layers is not None and li not in args.layers:
+            continue
         x = torch.randn(B, Ci, H, W, device="cuda")
-        off = torch.randn(B, 18, H, W, device="cuda") * 1.5
+        off = torch.randn(B, 18, H, W, device="cuda") * args.off_scale
+        if args.off_clamp > 0:
+            off = off.clamp(-args.off_clamp, args.off_clamp)
         m = torch.sigmoid(torch.randn(B, 9, H, W, device="cuda"))
         w = torch.randn(Co, Ci, 3, 3, device="cuda") / (3.0 * Ci ** 0.5)
         go = torch.randn(B, Co, H, W, device="cuda")
         a = run(x, off, m, w, go, True)
+        if args.quick:
+            torch.cuda.synchronize()
+            continue
         a2 = run(x, off, m, w, go, True)
         r = run(x, off, m, w, go, False)
         torch.cuda.synchronize()
@@ -56,9 +72,10 @@ def main():
             errs.append("%s %.2e/%.1f" % (name, (u - v).abs().max().item(), v.abs().max().item()))
         det = [bool((u == v).all().item()) for u, v in zip(a, a2)]
         t_tc = timeit(lambda: run(x, off, m, w, go, True))
+        t_nodx = timeit(lambda: run(x, off, m, w, go, True, False))
         t_fp = timeit(lambda: run(x, off, m, w, go, False), 3)
-        print("B%d %d@%dx%d->%d  tc %.3f ms  fp32 %.3f ms | %s | bit-identical dx,doff,dmask,dw,db: %s"
-              % (B, Ci, H, W, Co, t_tc, t_fp, "  ".join(errs), det), flush=True)
+        print("B%d %d@%dx%d->%d  tc %.3f ms (without dX %.3f)  fp32 %.3f ms | %s | bit-identical dx,doff,dmask,dw,db: %s"
+              % (B, Ci, H, W, Co, t_tc, t_nodx, t_fp, "  ".join(errs), det), flush=True)
 
 
 if __name__ == "__main__":
