@@ -566,7 +566,9 @@ __global__ void __launch_bounds__(256) k_dcn_bwd_dx_nchw(const float *__restrict
 
 // ------------------------------------------------------------------ dW = dY . col^T   (K = pixels)
 constexpr int WG_SAMPLERS = 16;
-constexpr int WG_THREADS = (TC_WARP_S0 + WG_SAMPLERS) * 32;   // warps 0-3 epilogue, 4 MMA, 5 TMA, 6-21 samplers
+constexpr int WG_GEOM = 4;                                    // warps 0-3: geometry producers (4 taps x 32 pixels per slice), then epilogue
+constexpr int WG_MR = 4;                                      // slices of geometry in flight
+constexpr int WG_THREADS = (TC_WARP_S0 + WG_SAMPLERS) * 32;   // warps 0-3 geometry + epilogue, 4 MMA, 5 TMA, 6-21 samplers
 constexpr uint32_t WG_SBO = 1040;                             // pitch of the A tile's 8-row groups (bank-conflict-free scalar stores)
 constexpr int WG_A_BYTES = (TC_TP / 8) * WG_SBO;              // 16640 per hi / lo tile
 __device__ __forceinline__ uint64_t wg_desc_a(uint32_t addr) {
@@ -649,9 +651,9 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
                     const float *__restrict__ gyk, float *__restrict__ wpart, const DcnShapeTc s, const BwdGeom g,
                     const WgGeom wg) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
-  __shared__ __align__(8) uint64_t a_full[3], b_full[3], empty[3], tm_full;
+  __shared__ __align__(8) uint64_t a_full[3], b_full[3], empty[3], tm_full, m_full[WG_MR], m_empty[WG_MR];
   __shared__ uint32_t tmem_base;
-  __shared__ BwdMetaTc wmeta[2][128];
+  __shared__ BwdMetaTc wmeta[WG_MR][128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rg = blockIdx.x % g.RG, split = blockIdx.x / g.RG;
   const int sl0 = (int)((long long)split * wg.n_slices / wg.splits), sl1 = (int)((long long)(split + 1) * wg.n_slices / wg.splits);
@@ -663,6 +665,7 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], WG_SAMPLERS); mbar_init(&b_full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&tm_full, 1);
+    for (int i = 0; i < WG_MR; ++i) { mbar_init(&m_full[i], WG_GEOM); mbar_init(&m_empty[i], WG_SAMPLERS); }
     mbar_fence_init();
   }
   if (warp == TC_WARP_MMA) {
@@ -676,11 +679,11 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
 
   if (warp >= TC_WARP_S0) {
     // =========================================================== samplers: the masked column tile, rows = channels
-    // Geometry of a slice's 4 taps x 32 pixels is computed once (threads 0..127 of the samplers, one slice ahead,
-    // double-buffered in shared memory); then task = (chunk ql, 4 pixels): lane = (pixel j, channel quad c4) gathers
-    // 4 corners x 16 bytes and stores its 4 channels x 1 pixel as scalars -- the 8-row groups of the A tile are
-    // pitched WG_SBO = 1040 bytes so that the 32 lanes of a store hit 32 different banks.
-    const int sw = warp - TC_WARP_S0, st = tid - TC_WARP_S0 * 32;
+    // task = (chunk ql, 4 pixels): lane = (pixel j, channel quad c4) gathers 4 corners x 16 bytes and stores its
+    // 4 channels x 1 pixel as scalars -- the 8-row groups of the A tile are pitched WG_SBO = 1040 bytes so that the 32
+    // lanes of a store hit 32 different banks.  Warps run free of each other: the geometry comes through a ring, the
+    // tile goes out through the 3-stage A ring.
+    const int sw = warp - TC_WARP_S0;
     const int j = lane >> 3, c4 = lane & 7;
     int t_meta[2], t_xc[2];
     uint32_t t_dst[2];
@@ -695,34 +698,24 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
       const int row = ql * 32 + c4 * 4;            // + i (i < 4 stays inside one 8-row group)
       t_dst[it] = (uint32_t)(row >> 3) * WG_SBO + (uint32_t)pg * TC_LBO + (uint32_t)(row & 7) * 16u + (uint32_t)j * 4u;
     }
-    // the geometry entry this thread produces (st < 128): chunk st / 32, pixel st % 32 of the slice
-    const int m_q = rg * 4 + (st >> 5);
-    const int m_bi = m_q / TC_NT, m_tap = (st < 128 && m_q < g.Q) ? m_q - m_bi * TC_NT : TC_NT;   // TC_NT = "no such tap"
-    const int m_gi = m_bi / s.cbs_pg;
-    auto geometry = [&](int bb, int sl_local) {
-      const int p = sl_local * TC_K + (st & 31);
-      const int ho = wg.wo_magic ? (int)__umulhi((unsigned)p, wg.wo_magic) : p / s.Wo;
-      return bwd_meta(s, offset + (long long)bb * s.off_bs, mask + (long long)bb * s.mask_bs, m_gi, m_tap, ho, p - ho * s.Wo);
-    };
     const int xs1 = Cp, xs2 = s.W * Cp, xs3 = (s.W + 1) * Cp;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int stage = 0, ph = 0, par = 0;
-    int b = sl0 / wg.spi, sll = sl0 - b * wg.spi;      // image and slice within the image
-    if (st < 128 && sl0 < sl1) wmeta[0][st] = geometry(b, sll);
-    named_bar_sync(1, WG_SAMPLERS * 32);
-    for (int sl = sl0; sl < sl1; ++sl) {
-      int nb_ = b, nsl = sll + 1;
-      if (nsl == wg.spi) { nsl = 0; ++nb_; }
-      BwdMetaTc nmeta;
-      if (st < 128 && sl + 1 < sl1) nmeta = geometry(nb_, nsl);       // its loads fly while this slice is sampled
+    int stage = 0, ph = 0, ms = 0, mph = 0;
+    int b = sl0 / wg.spi, sll = sl0 - b * wg.spi;      // image and slice within the image (of the slice being LOADED)
+    BwdMetaTc mt[2];
+    float4 xc[2][4];
+    // take the geometry of the next slice from the ring and issue its eight corner loads (a corner that is out of range,
+    // or a sample that is outside altogether -- all four flags clear, weights zero -- is simply not loaded)
+    auto load_slice = [&]() {
+      mbar_wait(&m_full[ms], (uint32_t)mph);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) mt[it] = wmeta[ms][t_meta[it]];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_tc(&m_empty[ms]);
+      if (++ms == WG_MR) { ms = 0; mph ^= 1; }
       const float *x_img = xt + (long long)b * HW * Cp;
-      // both tasks' eight corner loads are issued before anything is used; a corner that is out of range (or a sample
-      // that is outside altogether: all four flags clear, weights zero) is simply not loaded
-      BwdMetaTc mt[2];
-      float4 xc[2][4];
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
-        mt[it] = wmeta[par][t_meta[it]];
         const int flags = mt[it].packed;
         const int xo = ((flags >> 7) - (s.W + 1)) * Cp + t_xc[it];
         xc[it][0] = (flags & 1) ? __ldg(reinterpret_cast<const float4 *>(x_img + xo)) : z4;
@@ -730,6 +723,10 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
         xc[it][2] = (flags & 4) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs2))) : z4;
         xc[it][3] = (flags & 8) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs3))) : z4;
       }
+      if (++sll == wg.spi) { sll = 0; ++b; }
+    };
+    for (int sl = sl0; sl < sl1; ++sl) {
+      load_slice();
       float4 val[2];
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
@@ -758,11 +755,6 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
       __syncwarp();
       if (lane == 0) mbar_arrive_tc(&a_full[stage]);
       if (++stage == wg.stages) { stage = 0; ph ^= 1; }
-      if (st < 128 && sl + 1 < sl1) wmeta[par ^ 1][st] = nmeta;
-      named_bar_sync(1, WG_SAMPLERS * 32);
-      par ^= 1;
-      b = nb_;
-      sll = nsl;
     }
   } else if (warp == TC_WARP_TMA) {
     if (lane == 0) {
@@ -801,6 +793,67 @@ k_dcn_bwd_weight_tc(const float *__restrict__ xt, const float *__restrict__ offs
       umma_commit(&tm_full);
     }
   } else {
+    // =========================================================== warps 0-3 first produce the geometry: 4 taps x 32 pixels of a slice, one
+    // entry per thread, WG_MR slices ahead of the samplers (ring in shared memory, mbarrier hand-over); the offsets and
+    // mask of the next slice are fetched before the current entry is finished
+    const int st = tid;
+    const int m_q = rg * 4 + (st >> 5);
+    const int m_bi = m_q / TC_NT, m_tap = m_q < g.Q ? m_q - m_bi * TC_NT : TC_NT;     // TC_NT = "no such tap"
+    const int m_gi = m_bi / s.cbs_pg;
+    const bool m_ok = m_tap < KT;
+    const int ki = m_ok ? m_tap / s.kw : 0, kj = m_tap - ki * s.kw;
+    const int hb = ki * s.dh - s.ph, wb = kj * s.dw - s.pw;
+    const long long o_dy = ((long long)m_gi * 2 * KT + 2 * (m_ok ? m_tap : 0)) * HWo, o_m = ((long long)m_gi * KT + (m_ok ? m_tap : 0)) * HWo;
+    const int HWo_i = (int)HWo;
+    int b = sl0 / wg.spi, sll = sl0 - b * wg.spi;
+    float dy = 0.f, dx = 0.f, mk = 0.f;
+    auto fetch = [&](int bb, int sl_local) {
+      const int p = sl_local * TC_K + (st & 31);
+      dy = dx = mk = 0.f;
+      if (m_ok && p < HWo_i) {
+        const float *op = offset + (long long)bb * s.off_bs + o_dy + p;
+        dy = __ldg(op);
+        dx = __ldg(op + HWo);
+        mk = __ldg(mask + (long long)bb * s.mask_bs + o_m + p);
+      }
+    };
+    if (sl0 < sl1) fetch(b, sll);
+    int ms = 0, mph = 0;
+    for (int sl = sl0; sl < sl1; ++sl) {
+      const float cdy = dy, cdx = dx, cm = mk;
+      const int p = sll * TC_K + (st & 31);
+      int nb_ = b, nsl = sll + 1;
+      if (nsl == wg.spi) { nsl = 0; ++nb_; }
+      if (sl + 1 < sl1) fetch(nb_, nsl);
+      BwdMetaTc mt;
+      mt.lh = mt.lw = mt.m = 0.f;
+      mt.packed = 0;
+      if (m_ok && p < HWo_i) {
+        const int ho = wg.wo_magic ? (int)__umulhi((unsigned)p, wg.wo_magic) : p / s.Wo;
+        const int wo = p - ho * s.Wo;
+        const float h_im = (float)(ho * s.sh + hb) + cdy, w_im = (float)(wo * s.sw + wb) + cdx;
+        if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {     // dcn_v2_im2col_cuda.cu:165
+          const float hf = floorf(h_im), wf = floorf(w_im);
+          const int hl = (int)hf, wl = (int)wf;
+          int flags = 16;
+          if (hl >= 0 && wl >= 0) flags |= 1;
+          if (hl >= 0 && wl + 1 <= s.W - 1) flags |= 2;
+          if (hl + 1 <= s.H - 1 && wl >= 0) flags |= 4;
+          if (hl + 1 <= s.H - 1 && wl + 1 <= s.W - 1) flags |= 8;
+          mt.lh = h_im - hf;
+          mt.lw = w_im - wf;
+          mt.m = cm;
+          mt.packed = ((hl * s.W + wl + s.W + 1) << 7) | flags;
+        }
+      }
+      mbar_wait(&m_empty[ms], (uint32_t)(mph ^ 1));
+      wmeta[ms][st] = mt;
+      __syncwarp();
+      if (lane == 0) mbar_arrive_tc(&m_full[ms]);
+      if (++ms == WG_MR) { ms = 0; mph ^= 1; }
+      b = nb_;
+      sll = nsl;
+    }
     // epilogue: TMEM lane = row (chunk, channel), columns = output channels -> wpart[split][rg][row][co_r]
     const int qw = warp;
     float *dst = wpart + (((size_t)split * g.RG + rg) * 128 + qw * 32 + lane) * wg.co_r;
