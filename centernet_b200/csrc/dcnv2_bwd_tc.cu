@@ -317,100 +317,110 @@ k_dcn_bwd_offmask(const float *__restrict__ xt, const float *__restrict__ offset
     }
     __syncthreads();
     const int cb0 = gi * s.cbs_pg;
-    for (int tap = 0; tap < KT; ++tap) {
+    // This warp's items k = 0 .. 4 KT - 1: tap k / 4, pixels (warp + 8 (k % 4)) * 4 + j.  The five 16-byte loads of a
+    // (item, channel block) step are issued one step ahead -- across the item boundary too -- so the only exposed
+    // latency is the very first step's.
+    const int n_items = KT * 4;
+    struct Item { BwdMetaTc mt; int p, xo, dco; };
+    auto item = [&](int k) {
+      Item it;
+      const int tap = k >> 2, pp = (warp + 8 * (k & 3)) * 4 + j;
+      it.mt = meta[tap * TC_TP + pp];
+      it.p = (ty0 + (pp >> tws)) * s.Wo + tx0 + (pp & (s.tw - 1));            // 32-bit offsets within one image (host-checked)
+      it.xo = ((it.mt.packed >> 7) - (s.W + 1)) * Cp + cb0 * TC_CB;
+      it.dco = (it.p * g.Qp + cb0 * TC_NT + tap) * TC_CB;
+      return it;
+    };
+    float4 d, x1, x2, x3, x4;
+    auto issue = [&](int flags, int xo, int dco) {      // a corner out of range (or a sample outside: all flags clear) is not loaded
+      d = (flags & 16) ? __ldg(reinterpret_cast<const float4 *>(dc_img + dco)) : z4;
+      x1 = (flags & 1) ? __ldg(reinterpret_cast<const float4 *>(x_img + xo)) : z4;
+      x2 = (flags & 2) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs1))) : z4;
+      x3 = (flags & 4) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs2))) : z4;
+      x4 = (flags & 8) ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs3))) : z4;
+    };
+    Item cur = item(0);
+    issue(cur.mt.packed, cur.xo, cur.dco);
 #pragma unroll 1
-      for (int pq = warp; pq < TC_TP / 4; pq += 8) {
-        const int pp = pq * 4 + j;
-        const BwdMetaTc mt = meta[tap * TC_TP + pp];
-        const int flags = mt.packed & 127;
-        float am = 0.f, ah = 0.f, aw = 0.f;
-        const int p = (ty0 + (pp >> tws)) * s.Wo + tx0 + (pp & (s.tw - 1));   // 32-bit offsets within one image (host-checked)
+    for (int k = 0; k < n_items; ++k) {
+      const int tap = k >> 2;
+      Item nxt = cur;
+      if (k + 1 < n_items) nxt = item(k + 1);
+      const int flags = cur.mt.packed & 127;
+      const bool f1 = flags & 1, f2 = flags & 2, f3 = flags & 4, f4 = flags & 8;
+      const float lh = cur.mt.lh, lw = cur.mt.lw, hh = 1.f - lh, hw = 1.f - lw, m = cur.mt.m;
+      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+      const int base = (cur.mt.packed >> 7) - (s.W + 1);
+      int xo = cur.xo, dco = cur.dco;
+      float am = 0.f, ah = 0.f, aw = 0.f;
+#pragma unroll 1
+      for (int cbi = 0; cbi < s.cbs_pg; ++cbi) {
+        const float4 cd = d, c1 = x1, c2 = x2, c3 = x3, c4v = x4;
+        if (cbi + 1 < s.cbs_pg) issue(flags, xo + TC_CB, dco + TC_NT * TC_CB);
+        else if (k + 1 < n_items) issue(nxt.mt.packed, nxt.xo, nxt.dco);
         if (flags & 16) {
-          const int base = (mt.packed >> 7) - (s.W + 1);
-          const bool f1 = flags & 1, f2 = flags & 2, f3 = flags & 4, f4 = flags & 8;
-          const float lh = mt.lh, lw = mt.lw, hh = 1.f - lh, hw = 1.f - lw, m = mt.m;
-          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-          int dco = (p * g.Qp + cb0 * TC_NT + tap) * TC_CB;
-          int xo = base * Cp + cb0 * TC_CB;
-          float4 d = __ldg(reinterpret_cast<const float4 *>(dc_img + dco));
-          float4 x1 = f1 ? __ldg(reinterpret_cast<const float4 *>(x_img + xo)) : z4;
-          float4 x2 = f2 ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs1))) : z4;
-          float4 x3 = f3 ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs2))) : z4;
-          float4 x4 = f4 ? __ldg(reinterpret_cast<const float4 *>(x_img + (xo + xs3))) : z4;
-          for (int cbi = 0; cbi < s.cbs_pg; ++cbi) {
-            // next channel block in flight while this one is reduced
-            float4 nd = z4, n1 = z4, n2 = z4, n3 = z4, n4 = z4;
-            if (cbi + 1 < s.cbs_pg) {
-              nd = __ldg(reinterpret_cast<const float4 *>(dc_img + (dco + TC_NT * TC_CB)));
-              const int xn = xo + TC_CB;
-              if (f1) n1 = __ldg(reinterpret_cast<const float4 *>(x_img + xn));
-              if (f2) n2 = __ldg(reinterpret_cast<const float4 *>(x_img + (xn + xs1)));
-              if (f3) n3 = __ldg(reinterpret_cast<const float4 *>(x_img + (xn + xs2)));
-              if (f4) n4 = __ldg(reinterpret_cast<const float4 *>(x_img + (xn + xs3)));
-            }
-            // dMask (:297): dcol * unmasked bilinear sample
-            float4 v;
-            v.x = w1 * x1.x + w2 * x2.x + w3 * x3.x + w4 * x4.x;
-            v.y = w1 * x1.y + w2 * x2.y + w3 * x3.y + w4 * x4.y;
-            v.z = w1 * x1.z + w2 * x2.z + w3 * x3.z + w4 * x4.z;
-            v.w = w1 * x1.w + w2 * x2.w + w3 * x3.w + w4 * x4.w;
-            am += dot4(d, v);
-            // dOffset (:75-116, :299-302): dcol * mask * d(sample)/d{h,w}
-            const float4 dm = make_float4(d.x * m, d.y * m, d.z * m, d.w * m);
-            float4 gh, gw;
-            gh.x = -hw * x1.x - lw * x2.x + hw * x3.x + lw * x4.x;
-            gh.y = -hw * x1.y - lw * x2.y + hw * x3.y + lw * x4.y;
-            gh.z = -hw * x1.z - lw * x2.z + hw * x3.z + lw * x4.z;
-            gh.w = -hw * x1.w - lw * x2.w + hw * x3.w + lw * x4.w;
-            gw.x = -hh * x1.x + hh * x2.x - lh * x3.x + lh * x4.x;
-            gw.y = -hh * x1.y + hh * x2.y - lh * x3.y + lh * x4.y;
-            gw.z = -hh * x1.z + hh * x2.z - lh * x3.z + lh * x4.z;
-            gw.w = -hh * x1.w + hh * x2.w - lh * x3.w + lh * x4.w;
-            ah += dot4(dm, gh);
-            aw += dot4(dm, gw);
-            // dX (:182-239): the four corners receive dcol * mask * corner weight
-            if (dx_img) {
-              if (f1 && w1 != 0.f) red_add_v4(dx_img + xo, dm.x * w1, dm.y * w1, dm.z * w1, dm.w * w1);
-              if (f2 && w2 != 0.f) red_add_v4(dx_img + (xo + xs1), dm.x * w2, dm.y * w2, dm.z * w2, dm.w * w2);
-              if (f3 && w3 != 0.f) red_add_v4(dx_img + (xo + xs2), dm.x * w3, dm.y * w3, dm.z * w3, dm.w * w3);
-              if (f4 && w4 != 0.f) red_add_v4(dx_img + (xo + xs3), dm.x * w4, dm.y * w4, dm.z * w4, dm.w * w4);
-            } else if (gx_far && !(flags & 64)) {
-              const int cw = cbi * TC_CB + c4 * 4, cpg = s.Cin / s.dg;     // channel within the group (pad slots skipped)
-              float *gp = gx_far + ((long long)b * s.Cin + gi * cpg + cw) * HW + base;
-              const float dv[4] = {dm.x, dm.y, dm.z, dm.w};
+          // dMask (:297): dcol * unmasked bilinear sample
+          float4 v;
+          v.x = w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4v.x;
+          v.y = w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4v.y;
+          v.z = w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4v.z;
+          v.w = w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4v.w;
+          am += dot4(cd, v);
+          // dOffset (:75-116, :299-302): dcol * mask * d(sample)/d{h,w}
+          const float4 dm = make_float4(cd.x * m, cd.y * m, cd.z * m, cd.w * m);
+          float4 gh, gw;
+          gh.x = -hw * c1.x - lw * c2.x + hw * c3.x + lw * c4v.x;
+          gh.y = -hw * c1.y - lw * c2.y + hw * c3.y + lw * c4v.y;
+          gh.z = -hw * c1.z - lw * c2.z + hw * c3.z + lw * c4v.z;
+          gh.w = -hw * c1.w - lw * c2.w + hw * c3.w + lw * c4v.w;
+          gw.x = -hh * c1.x + hh * c2.x - lh * c3.x + lh * c4v.x;
+          gw.y = -hh * c1.y + hh * c2.y - lh * c3.y + lh * c4v.y;
+          gw.z = -hh * c1.z + hh * c2.z - lh * c3.z + lh * c4v.z;
+          gw.w = -hh * c1.w + hh * c2.w - lh * c3.w + lh * c4v.w;
+          ah += dot4(dm, gh);
+          aw += dot4(dm, gw);
+          // dX (:182-239): the four corners receive dcol * mask * corner weight
+          if (dx_img) {
+            if (f1 && w1 != 0.f) red_add_v4(dx_img + xo, dm.x * w1, dm.y * w1, dm.z * w1, dm.w * w1);
+            if (f2 && w2 != 0.f) red_add_v4(dx_img + (xo + xs1), dm.x * w2, dm.y * w2, dm.z * w2, dm.w * w2);
+            if (f3 && w3 != 0.f) red_add_v4(dx_img + (xo + xs2), dm.x * w3, dm.y * w3, dm.z * w3, dm.w * w3);
+            if (f4 && w4 != 0.f) red_add_v4(dx_img + (xo + xs3), dm.x * w4, dm.y * w4, dm.z * w4, dm.w * w4);
+          } else if (gx_far && !(flags & 64)) {
+            const int cw = cbi * TC_CB + c4 * 4, cpg = s.Cin / s.dg;     // channel within the group (pad slots skipped)
+            float *gp = gx_far + ((long long)b * s.Cin + gi * cpg + cw) * HW + base;
+            const float dv[4] = {dm.x, dm.y, dm.z, dm.w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (cw + i >= cpg) break;
-                float *q = gp + (long long)i * HW;
-                if (f1 && w1 != 0.f) atomicAdd(q, dv[i] * w1);
-                if (f2 && w2 != 0.f) atomicAdd(q + 1, dv[i] * w2);
-                if (f3 && w3 != 0.f) atomicAdd(q + s.W, dv[i] * w3);
-                if (f4 && w4 != 0.f) atomicAdd(q + s.W + 1, dv[i] * w4);
-              }
+            for (int i = 0; i < 4; ++i) {
+              if (cw + i >= cpg) break;
+              float *q = gp + (long long)i * HW;
+              if (f1 && w1 != 0.f) atomicAdd(q, dv[i] * w1);
+              if (f2 && w2 != 0.f) atomicAdd(q + 1, dv[i] * w2);
+              if (f3 && w3 != 0.f) atomicAdd(q + s.W, dv[i] * w3);
+              if (f4 && w4 != 0.f) atomicAdd(q + s.W + 1, dv[i] * w4);
             }
-            d = nd; x1 = n1; x2 = n2; x3 = n3; x4 = n4;
-            dco += TC_NT * TC_CB;
-            xo += TC_CB;
           }
         }
-        // fixed-order reduction over the 8 channel quads of a pixel
+        xo += TC_CB;
+        dco += TC_NT * TC_CB;
+      }
+      // fixed-order reduction over the 8 channel quads of a pixel
 #pragma unroll
-        for (int k = 4; k > 0; k >>= 1) {
-          am += __shfl_xor_sync(0xffffffffu, am, k);
-          ah += __shfl_xor_sync(0xffffffffu, ah, k);
-          aw += __shfl_xor_sync(0xffffffffu, aw, k);
-        }
-        // the gradients arrive zero-filled (dcn_v2_func.py:44-48) and every (tap, pixel) has exactly one writer:
-        // a plain store is the accumulation
-        if ((flags & 32) && c4 == 0) {
-          const int go = (gi * KT + tap) * (int)HWo + p;
-          if (gmask_img) gmask_img[go] = am;
-          if (goff_img) {
-            goff_img[2 * go - p] = ah;                 // channel 2 * (gi*KT + tap)
-            goff_img[2 * go - p + (int)HWo] = aw;
-          }
+      for (int sh = 4; sh > 0; sh >>= 1) {
+        am += __shfl_xor_sync(0xffffffffu, am, sh);
+        ah += __shfl_xor_sync(0xffffffffu, ah, sh);
+        aw += __shfl_xor_sync(0xffffffffu, aw, sh);
+      }
+      // the gradients arrive zero-filled (dcn_v2_func.py:44-48) and every (tap, pixel) has exactly one writer:
+      // a plain store is the accumulation
+      if ((flags & 32) && c4 == 0) {
+        const int go = (gi * KT + tap) * (int)HWo + cur.p;
+        if (gmask_img) gmask_img[go] = am;
+        if (goff_img) {
+          goff_img[2 * go - cur.p] = ah;                 // channel 2 * (gi*KT + tap)
+          goff_img[2 * go - cur.p + (int)HWo] = aw;
         }
       }
+      cur = nxt;
     }
   }
 }
