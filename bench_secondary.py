@@ -187,6 +187,30 @@ def run(dev, batches, K=100, steps=20):
                     t.grad = None
                 fn(*leaves).sum().backward()
             r["fwd_bwd_ms"] = round(timeit(fb, max(5, steps // 4), 2), 5)
+            # the backward alone (tcgen05: column-gradient GEMM + weight-gradient GEMM = twice the forward's flops)
+            bwd_ms = max(r["fwd_bwd_ms"] - ms, 1e-6)
+            r["backward"] = _tensor(bwd_ms, 2.0 * flops, tf, src,
+                                    config="DCNv2 backward (fwd_bwd_ms - forward; dX by 16-byte vector reductions, the other "
+                                           "four gradients bit-identical run to run)")
+            r["fwd_bwd_over_fwd"] = round(r["fwd_bwd_ms"] / ms, 2)
+            try:   # deterministic dX (cnb_dcnv2_set_deterministic): offsets held inside the gather window
+                from centernet_b200._lib import C as _C
+                leaves_d = [t.clone().requires_grad_(True) for t in (x, off.clamp(-1.9, 1.9), msk, w, bias)]
+
+                def fbd():
+                    for t in leaves_d:
+                        t.grad = None
+                    fn(*leaves_d).sum().backward()
+                import centernet_b200.dcn_v2_func as _f
+                prev = _f._DETERMINISTIC
+                _f._DETERMINISTIC = True
+                try:
+                    r["fwd_bwd_deterministic_ms"] = round(timeit(fbd, 3, 1), 5)
+                finally:
+                    _f._DETERMINISTIC = prev
+                    _C.dcnv2_set_deterministic(0)
+            except Exception as e:   # noqa: BLE001
+                r["fwd_bwd_deterministic_ms"] = "failed: %r" % (e,)
             if have_ref:
                 r["reference_gpu_fwd_ms"] = round(timeit(lambda: ref_gpu.dcn_v2_forward(x, off, msk, w, bias), 5, 2), 5)
                 go = torch.ones(b, co, hh, hh, device=dev)
