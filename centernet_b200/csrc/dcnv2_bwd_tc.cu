@@ -182,17 +182,20 @@ k_dcn_bwd_dcol_tc(const float *__restrict__ gyt, const float *__restrict__ wtt, 
       }
     }
   } else {
-    // epilogue: TMEM lane = pixel, 32 columns = the 32 channels of one chunk -> one 128-byte line of dcol
+    // epilogue: TMEM lane = pixel, 32 columns = the 32 channels of one chunk = one 128-byte line of dcol.  A thread
+    // holding a whole line would make every store instruction touch 32 lines (16 bytes each); the warp's 32 x 128 B
+    // block goes through shared memory instead (16-byte chunks XOR-swizzled by the pixel: conflict-free both ways)
+    // and leaves as 8 stores of 4 complete lines.
     const int qw = warp;
     const long long HWo = (long long)s.Ho * s.Wo;
+    unsigned char *stg = tc_smem + (size_t)BW_STAGES * BW_STAGE_BYTES + (size_t)qw * 4096;
+    const int ej = lane >> 3, ec = lane & 7;
     int acc = 0, aph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rg = item % g.RG, bt = item / g.RG;
       const int t = bt % g.tiles, b = bt / g.tiles;
-      const int pp = qw * 32 + lane;
-      const int ho = (t / s.tiles_x) * s.th + pp / s.tw, wo = (t % s.tiles_x) * s.tw + pp % s.tw;
-      const bool ok = ho < s.Ho && wo < s.Wo;
-      float *dst = dcol + (((long long)b * HWo + (long long)ho * s.Wo + wo) * g.Qp + rg * 4) * TC_CB;
+      const int ty0 = (t / s.tiles_x) * s.th, tx0 = (t % s.tiles_x) * s.tw;
+      float *dimg = dcol + (long long)b * HWo * g.Qp * TC_CB + (long long)rg * 4 * TC_CB + ec * 4;
       mbar_wait(&tm_full[acc], (uint32_t)aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tm + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * 128);
@@ -200,13 +203,22 @@ k_dcn_bwd_dcol_tc(const float *__restrict__ gyt, const float *__restrict__ wtt, 
       for (int ql = 0; ql < 4; ++ql) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)(ql * 32), v);
-        if (ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            reinterpret_cast<float4 *>(dst + ql * TC_CB)[j] =
-                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                            __uint_as_float(v[4 * j + 3]));
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4 *>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                          __uint_as_float(v[4 * c + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int pl = it * 4 + ej;                       // pixel within the warp's 32
+          const float4 val = *reinterpret_cast<const float4 *>(stg + pl * 128 + ((ec ^ (pl & 7)) << 4));
+          const int pp = qw * 32 + pl;
+          const int ho = ty0 + pp / s.tw, wo = tx0 + pp % s.tw;
+          if (ho < s.Ho && wo < s.Wo)
+            *reinterpret_cast<float4 *>(dimg + ((long long)ho * s.Wo + wo) * g.Qp * TC_CB + ql * TC_CB) = val;
         }
+        __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -237,6 +249,7 @@ constexpr int GX_TH = 8, GX_TW = 16;           // input positions per CTA
 constexpr int GX_WH = GX_TH + GX_WIN - 1, GX_WW = GX_TW + GX_WIN - 1;
 constexpr int GX_NC = GX_WIN * GX_WIN * TC_NT; // candidates per position (441)
 constexpr int GX_ROUNDS = (GX_NC + 31) / 32;
+constexpr int GX_LIST = GX_ROUNDS * 32;        // hit list capacity per warp (every candidate a hit)
 struct __align__(16) BwdMetaTc {
   float lh, lw, m;
   int packed;
@@ -440,6 +453,8 @@ k_dcn_bwd_dx_gather(const float *__restrict__ offset, const float *__restrict__ 
   BwdMetaTc *meta = reinterpret_cast<BwdMetaTc *>(gx_smem);                                  // [9][14][22]
   float(*tile)[GX_TH * GX_TW + 1] =
       reinterpret_cast<float(*)[GX_TH * GX_TW + 1]>(gx_smem + sizeof(BwdMetaTc) * TC_NT * GX_WH * GX_WW);   // [NCB*32][129]
+  float2 *mylist = reinterpret_cast<float2 *>(gx_smem + sizeof(BwdMetaTc) * TC_NT * GX_WH * GX_WW +
+                                              (size_t)NCB * TC_CB * (GX_TH * GX_TW + 1) * 4) + (threadIdx.x >> 5) * GX_LIST;   // per warp
   const int KT = s.kh * s.kw, cpg = s.Cin / s.dg;
   const long long HWo = (long long)s.Ho * s.Wo, HW = (long long)s.H * s.W;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -485,6 +500,8 @@ k_dcn_bwd_dx_gather(const float *__restrict__ offset, const float *__restrict__ 
           const int mbase = warp * GX_WW + px;
           const int posk = y * s.W + x + s.W + 1;
           const int dbase = (((ho0 + warp) * s.Wo + wo0 + px) * g.Qp + (gi * s.cbs_pg + cbg) * TC_NT) * TC_CB;
+          // pass 1: the hits of this position, in candidate order, as (weight, dcol offset) pairs
+          int cnt = 0;
 #pragma unroll
           for (int rnd = 0; rnd < GX_ROUNDS; ++rnd) {
             float wgt = 0.f;
@@ -501,36 +518,33 @@ k_dcn_bwd_dx_gather(const float *__restrict__ offset, const float *__restrict__ 
                 wgt *= e.m;
               }
             }
-            unsigned hits = __ballot_sync(0xffffffffu, hit);
-            while (hits) {        // warp-uniform: up to 4 hits per pass, their loads in flight together, added in lane order
-              float w[4], v[4][NCB];
-              int o[4], n = 0;
+            const unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if (hit) mylist[cnt + __popc(hits & ((1u << lane) - 1u))] = make_float2(wgt, __int_as_float(doff[rnd] + dbase));
+            cnt += __popc(hits);
+          }
+          __syncwarp();
+          // pass 2: eight hits' lines in flight at a time, added in list order (every lane = one channel)
+          for (int i0 = 0; i0 < cnt; i0 += 8) {
+            const int n = min(8, cnt - i0);
+            float2 e[8];
+            float v[8][NCB];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (hits) {
-                  const int src = __ffs(hits) - 1;
-                  hits &= hits - 1;
-                  w[k] = __shfl_sync(0xffffffffu, wgt, src);
-                  o[k] = __shfl_sync(0xffffffffu, doff[rnd], src) + dbase;
-                  n = k + 1;
-                }
+            for (int k = 0; k < 8; ++k)
+              if (k < n) {
+                e[k] = mylist[i0 + k];
+#pragma unroll
+                for (int cb = 0; cb < NCB; ++cb)
+                  if (cb < ncb) v[k][cb] = __ldg(dc_img + (__float_as_int(e[k].y) + cb * TC_NT * TC_CB));
               }
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < n) {
+            for (int k = 0; k < 8; ++k)
+              if (k < n) {
 #pragma unroll
-                  for (int cb = 0; cb < NCB; ++cb)
-                    if (cb < ncb) v[k][cb] = __ldg(dc_img + (o[k] + cb * TC_NT * TC_CB));
-                }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < n) {
-#pragma unroll
-                  for (int cb = 0; cb < NCB; ++cb)
-                    if (cb < ncb) acc[cb] = fmaf(w[k], v[k][cb], acc[cb]);
-                }
-            }
+                for (int cb = 0; cb < NCB; ++cb)
+                  if (cb < ncb) acc[cb] = fmaf(e[k].x, v[k][cb], acc[cb]);
+              }
           }
+          __syncwarp();
         }
 #pragma unroll
         for (int cb = 0; cb < NCB; ++cb) tile[cb * TC_CB + lane][warp * GX_TW + px] = acc[cb];
@@ -980,7 +994,7 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
   k_bwd_prep_w<<<g.RG * g.KS, 256, 0, stream>>>(weight, s, g, wtt);
   CNB_CHECK_LAUNCH("cnb_dcnv2_backward weight tiles");
   count_launch();
-  const size_t smem = (size_t)BW_STAGES * BW_STAGE_BYTES;
+  const size_t smem = (size_t)BW_STAGES * BW_STAGE_BYTES + 4 * 4096;     // operand ring + the epilogue warps' staging
   static thread_local int dev_done = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1004,11 +1018,12 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
     if (gather) {
       const int ptx = (w + GX_TW - 1) / GX_TW, pty = (h + GX_TH - 1) / GX_TH;
       const int ncb = s.cbs_pg >= 2 ? 2 : 1;
-      const size_t gsm = sizeof(BwdMetaTc) * TC_NT * GX_WH * GX_WW + (size_t)ncb * TC_CB * (GX_TH * GX_TW + 1) * 4;
+      const size_t gsm = sizeof(BwdMetaTc) * TC_NT * GX_WH * GX_WW + (size_t)ncb * TC_CB * (GX_TH * GX_TW + 1) * 4 +
+                         (size_t)8 * GX_LIST * sizeof(float2);
       static thread_local int gdev_done = -1;
       if (gdev_done != dev) {
-        CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_dx_gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_dx_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_dx_gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_dx_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         gdev_done = dev;
       }
       if (ncb == 2)
