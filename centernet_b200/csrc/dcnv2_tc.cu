@@ -20,9 +20,10 @@
 // Sampling: the input is read from a channels-last copy [B][H*W][Cin/32][32] (k_dcn_nhwc; skipped when the
 // caller's tensor already is channels-last).  A warp gather covers 4 pixels x 32 channels with
 // lane = pixel * 8 + quad, so each quarter-warp -- the unit the L1 data pipe serves for 16-byte accesses --
-// reads ONE fully used 128-byte line (4 wavefronts per gather).  The UMMA tile wants the opposite lane order
-// (a quarter-warp = 8 rows of one k-chunk), so the reduced values are transposed across the warp with
-// shuffles before the conflict-free 16-byte stores.
+// reads ONE fully used 128-byte line (4 wavefronts per gather).  Each lane then holds exactly one 16-byte k-chunk of
+// the K-major UMMA tile; the tile's k-chunks are pitched 144 bytes (LBO in the descriptor) instead of 128, which puts
+// the eight chunks a quarter-warp stores into eight different bank groups -- conflict-free without a transpose
+// (round 1 transposed across the warp with 16 shuffles; same speed, fewer instructions).
 //
 // Small maps (16x16, 8x8): too few tiles to fill 148 SMs, so the channel blocks of an item are split over
 // several CTAs (split-K); the partial sums go to the workspace and k_dcn_reduce adds them in a fixed order
@@ -136,7 +137,7 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
                  float *__restrict__ part, const DcnShapeTc s) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   constexpr int B_BYTES = CO_T * TC_K * 4;                  // one hi or lo weight tile
-  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  constexpr int STAGE_BYTES = 2 * FW_A_BYTES + 2 * B_BYTES;
   TapMetaTc *meta = reinterpret_cast<TapMetaTc *>(tc_smem + (size_t)STAGES * STAGE_BYTES);     // [9][128]
   __shared__ __align__(8) uint64_t a_full[STAGES], b_full[STAGES], empty[STAGES], tm_full[2], tm_empty[2];
   __shared__ uint32_t tmem_base;
@@ -236,25 +237,18 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
           // the ring slot must have been drained by the MMAs that last read it
           mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
           unsigned char *a_hi = tc_smem + (size_t)stage * STAGE_BYTES;
-          unsigned char *a_lo = a_hi + TC_A_BYTES;
-          // transpose: store instruction j writes (row = lane & 7, quad = (lane >> 3) + 4 j); that value lives in
-          // lane (row & 3) * 8 + quad, in v0 for rows 0-3 and v1 for rows 4-7
-          const int row = lane & 7;
-          const bool upper = row >= 4;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int quad = (lane >> 3) + 4 * j;
-            const int src = (row & 3) * 8 + quad;
-            float4 a, c;
-            a.x = __shfl_sync(0xffffffffu, v0.x, src); c.x = __shfl_sync(0xffffffffu, v1.x, src);
-            a.y = __shfl_sync(0xffffffffu, v0.y, src); c.y = __shfl_sync(0xffffffffu, v1.y, src);
-            a.z = __shfl_sync(0xffffffffu, v0.z, src); c.z = __shfl_sync(0xffffffffu, v1.z, src);
-            a.w = __shfl_sync(0xffffffffu, v0.w, src); c.w = __shfl_sync(0xffffffffu, v1.w, src);
-            const float4 v = upper ? c : a;
-            const float4 h4 = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            const uint32_t off = tc_tile_off(sw * 8 + row, quad * 4);
-            *reinterpret_cast<float4 *>(a_hi + off) = h4;
-            *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h4.x, v.y - h4.y, v.z - h4.z, v.w - h4.w);
+          unsigned char *a_lo = a_hi + FW_A_BYTES;
+          // each lane already holds one 16-byte k-chunk of the K-major tile: (row, chunk sq).  The k-chunks of the A tile
+          // are pitched FW_LBO = 144 bytes (not 128), so the eight chunks of a row -- one quarter-warp -- fall into eight
+          // different 16-byte bank groups: conflict-free stores without a transpose
+          {
+            const float4 h0 = make_float4(tf32_hi(v0.x), tf32_hi(v0.y), tf32_hi(v0.z), tf32_hi(v0.w));
+            const float4 h1 = make_float4(tf32_hi(v1.x), tf32_hi(v1.y), tf32_hi(v1.z), tf32_hi(v1.w));
+            const uint32_t off0 = (uint32_t)sw * FW_SBO + (uint32_t)sq * FW_LBO + (uint32_t)sp * 16u, off1 = off0 + 64u;
+            *reinterpret_cast<float4 *>(a_hi + off0) = h0;
+            *reinterpret_cast<float4 *>(a_lo + off0) = make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w);
+            *reinterpret_cast<float4 *>(a_hi + off1) = h1;
+            *reinterpret_cast<float4 *>(a_lo + off1) = make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA reads)
           __syncwarp();
@@ -272,7 +266,7 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
         for (int bi = it.b0; bi < it.b1; ++bi) {
           for (int tap = 0; tap < TC_NT; ++tap) {
             mbar_wait(&empty[stage], (uint32_t)(ph ^ 1));
-            unsigned char *b_hi = tc_smem + (size_t)stage * STAGE_BYTES + 2 * TC_A_BYTES;
+            unsigned char *b_hi = tc_smem + (size_t)stage * STAGE_BYTES + 2 * FW_A_BYTES;
             const float *src = wtiles + (((size_t)it.cot * s.nb + bi) * TC_NT + tap) * 2 * (size_t)CO_T * TC_K;
             mbar_expect_tx(&b_full[stage], 2u * B_BYTES);
             for (uint32_t off = 0; off < 2u * B_BYTES; off += 8192u)
@@ -297,12 +291,13 @@ k_dcn_forward_tc(const float *__restrict__ xt, const float *__restrict__ offset,
           mbar_wait(&a_full[stage], (uint32_t)ph);
           mbar_wait(&b_full[stage], (uint32_t)ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ah = smem_u32(tc_smem + (size_t)stage * STAGE_BYTES), al = ah + TC_A_BYTES;
-          const uint32_t bh = al + TC_A_BYTES, bl = bh + B_BYTES;
+          const uint32_t ah = smem_u32(tc_smem + (size_t)stage * STAGE_BYTES), al = ah + FW_A_BYTES;
+          const uint32_t bh = al + FW_A_BYTES, bl = bh + B_BYTES;
 #pragma unroll
           for (int ks = 0; ks < TC_K / 8; ++ks) {   // one UMMA per 8 k (two 16-byte k-chunks), 3 per step (3xTF32)
             const uint32_t koff = (uint32_t)ks * 2u * TC_LBO;
-            const uint64_t dah = tc_desc(ah + koff), dal = tc_desc(al + koff);
+            const uint32_t koff_a = (uint32_t)ks * 2u * FW_LBO;
+            const uint64_t dah = fw_desc_a(ah + koff_a), dal = fw_desc_a(al + koff_a);
             const uint64_t dbh = tc_desc(bh + koff), dbl = tc_desc(bl + koff);
             const uint32_t acc0 = (ch > 0 || ks > 0) ? 1u : 0u;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -424,7 +419,7 @@ int dcn_to_channels_last(const float *x, float *xt, const DcnShapeTc &s, cudaStr
 template <int CO_T, int STAGES>
 static int launch_fwd(const float *xt, const float *offset, const float *mask, const float *wtiles, const float *bias,
                       float *output, float *part, const DcnShapeTc &s, cudaStream_t stream) {
-  const size_t smem = (size_t)STAGES * (2 * TC_A_BYTES + 2 * CO_T * TC_K * 4) + sizeof(TapMetaTc) * TC_NT * TC_TP;
+  const size_t smem = (size_t)STAGES * (2 * FW_A_BYTES + 2 * CO_T * TC_K * 4) + sizeof(TapMetaTc) * TC_NT * TC_TP;
   static thread_local int dev_done = -1;
   int dev = 0;
   cudaGetDevice(&dev);

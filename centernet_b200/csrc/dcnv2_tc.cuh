@@ -20,6 +20,11 @@ constexpr uint32_t TC_LBO = 128;            // bytes between consecutive k-chunk
 constexpr uint32_t TC_SBO = TC_KC * 128;    // bytes between 8-row groups
 constexpr int TC_A_BYTES = TC_TP * TC_K * 4;  // 16384 per hi / lo tile
 
+// A tile of the forward sampler: the same K-major core-matrix layout with the k-chunks pitched 144 bytes apart
+constexpr uint32_t FW_LBO = 144;                    // bytes between consecutive k-chunks (8 rows x 16 B + 16 B of padding)
+constexpr uint32_t FW_SBO = TC_KC * FW_LBO;         // bytes between 8-row groups (1152)
+constexpr int FW_A_BYTES = (TC_TP / 8) * FW_SBO;    // 18432 per hi / lo tile
+
 struct DcnShapeTc {
   int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo;
   int co_t;       // output channels per item (64 or 128)
@@ -51,6 +56,14 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr) {
   d |= (uint64_t)((TC_LBO >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((TC_SBO >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout_type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ uint64_t fw_desc_a(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((FW_LBO >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((FW_SBO >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
