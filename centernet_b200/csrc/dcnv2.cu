@@ -504,10 +504,11 @@ extern std::atomic<int> g_dcn_deterministic;
 int dcn_backward_data_tc(const float *input, const float *offset, const float *mask, const float *weight,
                          const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask, int b,
                          int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
-                         int dg, void *workspace, cudaStream_t stream, int xt_ready);
+                         int dg, void *workspace, cudaStream_t stream, int xt_ready, int layout);
 int dcn_backward_weight_tc(const float *input, const float *offset, const float *mask, const float *grad_output,
                            float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw,
-                           int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream, int xt_ready);
+                           int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream, int xt_ready,
+                           int layout);
 }
 
 using namespace cnb;
@@ -646,11 +647,12 @@ int cnb_dcnv2_forward(const float *input, const float *offset, const float *mask
   return CNB_OK;
 }
 
-int cnb_dcnv2_backward(const float *input, const float *offset, const float *mask, const float *weight,
-                       const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask,
-                       float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw,
-                       int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_groups,
-                       void *workspace, size_t workspace_bytes, void *stream_) {
+static int dcnv2_backward_impl(const float *input, const float *offset, const float *mask, const float *weight,
+                               const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask,
+                               float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh,
+                               int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                               int deformable_groups, void *workspace, size_t workspace_bytes, void *stream_,
+                               int layout) {
   CNB_REQUIRE(input && offset && mask && weight && grad_output, CNB_EINVAL, "cnb_dcnv2_backward: null pointer");
   DcnShape s;
   int rc = check_shape("cnb_dcnv2_backward", b, cin, h, w, cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h,
@@ -667,10 +669,19 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
                           ? dcn_tc_bwd_workspace_bytes(b, cin, h, w, cout, kh, kw, stride_h, pad_h, dil_h, deformable_groups)
                           : 0;
   const bool tc = workspace && need > 0 && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0;
+  if (layout) {   // channels-last input / grad_input: tensor-core path only, whole 32-channel blocks, scatter form of dX
+    CNB_REQUIRE(tc && cout <= 256, CNB_EUNSUPPORTED, "cnb_dcnv2_backward_ex: channels-last tensors need the tensor-core path "
+                "(workspace of cnb_dcnv2_backward_workspace_bytes, at most 9 taps, isotropic stride/pad/dilation, cout <= 256)");
+    CNB_REQUIRE((cin / deformable_groups) % 32 == 0, CNB_EUNSUPPORTED,
+                "cnb_dcnv2_backward_ex: channels-last tensors need cin / deformable_groups to be a multiple of 32");
+    CNB_REQUIRE(!(layout & 2) || !cnb_dcnv2_get_deterministic(), CNB_EUNSUPPORTED,
+                "cnb_dcnv2_backward_ex: a channels-last grad_input is not available in deterministic mode");
+    if (!grad_input) layout &= ~2;
+  }
   if (tc && (grad_input || grad_offset || grad_mask)) {
     rc = dcn_backward_data_tc(input, offset, mask, weight, grad_output, grad_input, grad_offset, grad_mask, b, cin, h, w,
                               cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups, workspace,
-                              stream, 0);
+                              stream, 0, layout);
     if (rc != CNB_OK) return rc;
   } else if (grad_input || grad_offset || grad_mask) {
     const size_t smem = sizeof(BwdMeta) * DCN_KT_MAX * DCN_TP + sizeof(float) * KC * DCN_TP +
@@ -691,7 +702,7 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
   if (tc && grad_weight && cout <= 256) {
     rc = dcn_backward_weight_tc(input, offset, mask, grad_output, grad_weight, grad_bias, b, cin, h, w, cout, kh, kw, stride_h,
                                 stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups, workspace, stream,
-                                (grad_input || grad_offset || grad_mask) ? 1 : 0);
+                                (grad_input || grad_offset || grad_mask) ? 1 : 0, layout);
     if (rc != CNB_OK) return rc;
     grad_bias = nullptr;   // done by the weight pass
   } else if (grad_weight) {
@@ -717,6 +728,27 @@ int cnb_dcnv2_backward(const float *input, const float *offset, const float *mas
   }
   count_launch(launches);
   return CNB_OK;
+}
+
+int cnb_dcnv2_backward(const float *input, const float *offset, const float *mask, const float *weight,
+                       const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask,
+                       float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw,
+                       int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_groups,
+                       void *workspace, size_t workspace_bytes, void *stream_) {
+  return dcnv2_backward_impl(input, offset, mask, weight, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+                             grad_bias, b, cin, h, w, cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w,
+                             deformable_groups, workspace, workspace_bytes, stream_, 0);
+}
+
+int cnb_dcnv2_backward_ex(const float *input, int input_channels_last, const float *offset, const float *mask,
+                          const float *weight, const float *grad_output, float *grad_input,
+                          int grad_input_channels_last, float *grad_offset, float *grad_mask, float *grad_weight,
+                          float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw, int stride, int pad,
+                          int dil, int deformable_groups, void *workspace, size_t workspace_bytes, void *stream_) {
+  return dcnv2_backward_impl(input, offset, mask, weight, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+                             grad_bias, b, cin, h, w, cout, kh, kw, stride, stride, pad, pad, dil, dil, deformable_groups,
+                             workspace, workspace_bytes, stream_,
+                             (input_channels_last ? 1 : 0) | (grad_input_channels_last ? 2 : 0));
 }
 
 }  // extern "C"

@@ -970,7 +970,9 @@ size_t dcn_tc_bwd_workspace_bytes(int b, int cin, int h, int w, int cout, int kh
 int dcn_backward_data_tc(const float *input, const float *offset, const float *mask, const float *weight,
                          const float *grad_output, float *grad_input, float *grad_offset, float *grad_mask, int b,
                          int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
-                         int dg, void *workspace, cudaStream_t stream, int xt_ready) {
+                         int dg, void *workspace, cudaStream_t stream, int xt_ready, int layout) {
+  // layout bit 0: `input` already is channels-last [b][h*w][cin]; bit 1: so is grad_input (both need cin/dg % 32 == 0,
+  // checked by the caller): the layout passes and the channels-last scratch copies are skipped
   DcnShapeTc s;
   fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
   const BwdGeom g = bwd_geom(s);
@@ -978,19 +980,21 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
   char *wp = reinterpret_cast<char *>(workspace);
   float *xt = reinterpret_cast<float *>(wp);  wp += bw_xt_bytes(s);
   float *dxt = reinterpret_cast<float *>(wp); wp += bw_xt_bytes(s);
+  const float *xsrc = (layout & 1) ? input : xt;
+  if (layout & 2) dxt = grad_input;
   float *wtt = reinterpret_cast<float *>(wp); wp += bw_wtt_bytes(g);
   float *gyt = reinterpret_cast<float *>(wp); wp += align_up((size_t)bc * bw_gyt_bytes_per_image(g), 256);
   float *dcol = reinterpret_cast<float *>(wp);
   const long long HW = (long long)h * w, HWo = (long long)s.Ho * s.Wo;
 
   int rc = CNB_OK;
-  if (!xt_ready) rc = dcn_to_channels_last(input, xt, s, stream);
+  if (!xt_ready && !(layout & 1)) rc = dcn_to_channels_last(input, xt, s, stream);
   if (rc != CNB_OK) return rc;
   // default: every sample is scattered into a channels-last dX (16-byte vector reductions) and added to grad_input at
   // the end; deterministic mode (cnb_dcnv2_set_deterministic, stride 1): near samples by the gather, the rest by atomics
   // straight into grad_input
   const bool gather = grad_input && sh == 1 && sw == 1 && w >= 2 && g_dcn_deterministic.load(std::memory_order_relaxed) != 0;
-  if (grad_input && !gather) CNB_CUDA(cudaMemsetAsync(dxt, 0, (size_t)b * HW * s.nb * TC_CB * 4, stream));
+  if (grad_input && !gather && !(layout & 2)) CNB_CUDA(cudaMemsetAsync(dxt, 0, (size_t)b * HW * s.nb * TC_CB * 4, stream));
   k_bwd_prep_w<<<g.RG * g.KS, 256, 0, stream>>>(weight, s, g, wtt);
   CNB_CHECK_LAUNCH("cnb_dcnv2_backward weight tiles");
   count_launch();
@@ -1011,7 +1015,7 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
     const int grid = n_items < num_sms() ? n_items : num_sms();
     k_dcn_bwd_dcol_tc<<<grid, BW_THREADS, smem, stream>>>(gyt, wtt, dcol, s, g, n_items);
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward column gradient (tcgen05)");
-    k_dcn_bwd_offmask<3><<<nbimg * g.tiles, 256, 0, stream>>>(xt, offset, mask, dcol, (grad_input && !gather) ? dxt : nullptr,
+    k_dcn_bwd_offmask<3><<<nbimg * g.tiles, 256, 0, stream>>>(xsrc, offset, mask, dcol, (grad_input && !gather) ? dxt : nullptr,
                                                               grad_offset, grad_mask, gather ? grad_input : nullptr, s, g, b0);
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward offset/mask gradient");
     count_launch(3);
@@ -1034,7 +1038,7 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
       count_launch();
     }
   }
-  if (grad_input && !gather) {
+  if (grad_input && !gather && !(layout & 2)) {
     dim3 tgrid((unsigned)((HW + 31) / 32), (unsigned)((cin + 63) / 64), (unsigned)b);
     k_dcn_bwd_dx_nchw<<<tgrid, 256, 0, stream>>>(dxt, grad_input, s);
     CNB_CHECK_LAUNCH("cnb_dcnv2_backward input gradient");
@@ -1047,7 +1051,8 @@ int dcn_backward_data_tc(const float *input, const float *offset, const float *m
 // already written by dcn_backward_data_tc on this stream.
 int dcn_backward_weight_tc(const float *input, const float *offset, const float *mask, const float *grad_output,
                            float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int kh, int kw, int sh, int sw,
-                           int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream, int xt_ready) {
+                           int ph, int pw, int dh, int dw, int dg, void *workspace, cudaStream_t stream, int xt_ready,
+                           int layout) {
   DcnShapeTc s;
   fill_shape(&s, b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
   const BwdGeom g = bwd_geom(s);
@@ -1057,7 +1062,8 @@ int dcn_backward_weight_tc(const float *input, const float *offset, const float 
   float *gyk = reinterpret_cast<float *>(wp); wp += bw_gyk_bytes(wg);
   float *wpart = reinterpret_cast<float *>(wp); wp += bw_wpart_bytes(g, wg);
   float *bpart = reinterpret_cast<float *>(wp);
-  if (!xt_ready) {
+  const float *xsrc = (layout & 1) ? input : xt;
+  if (!xt_ready && !(layout & 1)) {
     const int rc = dcn_to_channels_last(input, xt, s, stream);
     if (rc != CNB_OK) return rc;
   }
@@ -1072,7 +1078,7 @@ int dcn_backward_weight_tc(const float *input, const float *offset, const float 
     CNB_CUDA(cudaFuncSetAttribute(k_dcn_bwd_weight_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 66048));
     dev_done = dev;
   }
-  k_dcn_bwd_weight_tc<<<g.RG * wg.splits, WG_THREADS, smem, stream>>>(xt, offset, mask, gyk, wpart, s, g, wg);
+  k_dcn_bwd_weight_tc<<<g.RG * wg.splits, WG_THREADS, smem, stream>>>(xsrc, offset, mask, gyk, wpart, s, g, wg);
   CNB_CHECK_LAUNCH("cnb_dcnv2_backward weight gradient (tcgen05)");
   const long long total = (long long)g.RG * 128 * wg.co_r;
   k_dcn_bwd_wreduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(wpart, grad_weight, s, g, wg);

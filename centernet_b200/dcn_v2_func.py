@@ -75,7 +75,10 @@ class _DCNv2(Function):
             input.dtype == torch.float32 and input.is_contiguous(memory_format=torch.channels_last) and \
             not input.is_contiguous()
         need_grad = any(ctx.needs_input_grad[:5])
-        x = f32c(input) if (need_grad or not nhwc) else None      # NCHW copy only when somebody needs it
+        # the backward takes a channels_last input as it is too (cnb_dcnv2_backward_ex): no NCHW copy is kept for it
+        x_cl = nhwc and need_grad and cout <= 256 and \
+            C.dcnv2_backward_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding, dilation, deformable_groups) > 0
+        x = f32c(input) if ((need_grad and not x_cl) or not nhwc) else None      # NCHW copy only when somebody needs it
         if _FORCE_FP32 or kt > 9:
             C.dcnv2_forward(ptr(x), ptr(off), ptr(msk), ptr(w), ptr(b), ptr(out), n, cin, h, wd, cout, kh, kw,
                             stride, stride, padding, padding, dilation, dilation, deformable_groups, 0, 0,
@@ -90,7 +93,8 @@ class _DCNv2(Function):
                                      cout, kh, kw, stride, stride, padding, padding, dilation, dilation,
                                      deformable_groups, ptr(ws), ws.numel(), stream_ptr(off))
         if need_grad:
-            ctx.save_for_backward(x, off, msk, w, b)
+            ctx.save_for_backward(input if x_cl else x, off, msk, w, b)
+        ctx.x_cl = bool(x_cl)
         ctx.cfg = (stride, padding, dilation, deformable_groups)
         return out
 
@@ -103,22 +107,31 @@ class _DCNv2(Function):
         go = f32c(grad_output)
         n, cin, h, wd = [int(v) for v in x.shape]
         cout, _, kh, kw = [int(v) for v in w.shape]
-        # zero-filled, accumulated into -- dcn_v2_func.py:44-48
+        # grad_input by the fixed-order gather when the user asked torch for deterministic algorithms (or CNB_DCN_DETERMINISTIC=1)
+        det = bool(_DETERMINISTIC or torch.are_deterministic_algorithms_enabled())
+        C.dcnv2_set_deterministic(int(det))
+        x_cl = ctx.x_cl and not det and not _FORCE_FP32
+        if ctx.x_cl and not x_cl:
+            x = x.contiguous()          # the gather (and the fp32 kernels) work on NCHW
+        # zero-filled, accumulated into -- dcn_v2_func.py:44-48 (zeros_like keeps a channels_last input's layout)
         gx = torch.zeros_like(x)
         goff = torch.zeros_like(off)
         gmsk = torch.zeros_like(msk)
         gw = torch.zeros_like(w)
         gb = torch.zeros_like(b) if b is not None else None
-        # grad_input by the fixed-order gather when the user asked torch for deterministic algorithms (or CNB_DCN_DETERMINISTIC=1)
-        C.dcnv2_set_deterministic(int(_DETERMINISTIC or torch.are_deterministic_algorithms_enabled()))
-        ws, wsb = 0, 0
+        wsbuf, wsb = None, 0
         if not _FORCE_FP32:
             wsb = C.dcnv2_backward_workspace_bytes(n, cin, cout, h, wd, kh, kw, stride, padding, dilation, dg)
             if wsb:
-                ws = ptr(workspace(wsb, x.device))
-        C.dcnv2_backward(ptr(x), ptr(off), ptr(msk), ptr(w), ptr(go), ptr(gx), ptr(goff), ptr(gmsk), ptr(gw), ptr(gb),
-                         n, cin, h, wd, cout, kh, kw, stride, stride, padding, padding, dilation, dilation, dg,
-                         ws, wsb, stream_ptr(x))
+                wsbuf = workspace(wsb, x.device)
+        if x_cl:
+            C.dcnv2_backward_ex(ptr(x), 1, ptr(off), ptr(msk), ptr(w), ptr(go), ptr(gx), 1, ptr(goff), ptr(gmsk), ptr(gw),
+                                ptr(gb), n, cin, h, wd, cout, kh, kw, stride, padding, dilation, dg, ptr(wsbuf), wsb,
+                                stream_ptr(x))
+        else:
+            C.dcnv2_backward(ptr(x), ptr(off), ptr(msk), ptr(w), ptr(go), ptr(gx), ptr(goff), ptr(gmsk), ptr(gw), ptr(gb),
+                             n, cin, h, wd, cout, kh, kw, stride, stride, padding, padding, dilation, dilation, dg,
+                             ptr(wsbuf) if wsbuf is not None else 0, wsb, stream_ptr(x))
         return gx, goff, gmsk, gw, gb, None, None, None, None
 
 

@@ -252,6 +252,17 @@ int cnb_dcnv2_forward_fused(const float *input, int input_channels_last, const f
                             void *workspace, size_t workspace_bytes, void *stream);
 size_t cnb_dcnv2_backward_workspace_bytes(int b, int cin, int cout, int h, int w, int kh, int kw,
                                           int stride, int pad, int dil, int dg);
+/* The backward for a channels-last pipeline (torch channels_last): input_channels_last / grad_input_channels_last
+ * != 0 say the tensor is [b][h*w][cin]; the re-layout pass of the input, the zero-fill and the final NCHW pass of
+ * grad_input disappear (grad_input still arrives zero-filled).  Tensor-core path only: needs the workspace,
+ * cin / deformable_groups % 32 == 0, cout <= 256, non-deterministic dX; CNB_EUNSUPPORTED otherwise. */
+int cnb_dcnv2_backward_ex(const float *input, int input_channels_last, const float *offset,
+                          const float *mask, const float *weight, const float *grad_output,
+                          float *grad_input, int grad_input_channels_last,
+                          float *grad_offset, float *grad_mask, float *grad_weight, float *grad_bias,
+                          int b, int cin, int h, int w, int cout, int kh, int kw,
+                          int stride, int pad, int dil, int deformable_groups,
+                          void *workspace, size_t workspace_bytes, void *stream);
 /* grad_offset, grad_mask, grad_weight and grad_bias of the tensor-core backward are bit-identical run to run.
  * grad_input is by default scattered with (vector) atomics like the reference's col2im
  * (dcn_v2_im2col_cuda.cu:182-239), i.e. its last bits depend on the order the adds land.  on != 0 selects a

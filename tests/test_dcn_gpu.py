@@ -147,6 +147,27 @@ def test_backward_deterministic_mode(B, Ci, H, W, Co, dg):
         assert torch.equal(u, v), name + " not bit-identical run to run in deterministic mode"
 
 
+@pytest.mark.parametrize("B,Ci,H,W,Co", [(2, 64, 24, 40, 64), (2, 128, 17, 19, 96)])
+def test_backward_channels_last(B, Ci, H, W, Co):
+    """A channels_last activation goes through forward (sampled in place) and backward (cnb_dcnv2_backward_ex: input and
+    grad_input channels-last, no layout passes); results equal the NCHW path, grad_input comes back channels_last."""
+    from centernet_b200.dcn_v2_func import DCNv2Function
+    x, off, m, w, b = [t.cuda() for t in make(B, Ci, H, W, Co, 1, 1, seed=17, off_scale=1.5)]
+    go = torch.randn(B, Co, H, W, generator=torch.Generator().manual_seed(8)).cuda()
+    ref = [t.clone().requires_grad_(True) for t in (x, off, m, w, b)]
+    out_ref = DCNv2Function(1, 1, 1, 1)(*ref)
+    (out_ref * go).sum().backward()
+    cl = [x.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)] + \
+        [t.clone().requires_grad_(True) for t in (off, m, w, b)]
+    out = DCNv2Function(1, 1, 1, 1)(*cl)
+    (out * go).sum().backward()
+    assert (out - out_ref).abs().max().item() <= 1e-5
+    assert cl[0].grad.is_contiguous(memory_format=torch.channels_last)
+    for name, u, v in zip(("input", "offset", "mask", "weight", "bias"), cl, ref):
+        scale = max(1.0, v.grad.abs().max().item())
+        assert (u.grad - v.grad).abs().max().item() <= 1e-4 * scale, (name, (u.grad - v.grad).abs().max().item())
+
+
 def test_dcn_module_and_state_dict_names():
     from centernet_b200.dcn_v2 import DCN
     dcn = DCN(16, 8, kernel_size=(3, 3), stride=1, padding=1, deformable_groups=1).cuda()

@@ -27,6 +27,19 @@ def run(x, off, m, w, go, tc, want_dx=True):
     return gx, goff, gm, gw, gb
 
 
+def run_cl(xcl, off, m, w, go):
+    """cnb_dcnv2_backward_ex: input and grad_input channels-last (no layout passes)."""
+    B, Ci, H, W = xcl.shape
+    Co = w.shape[0]
+    gx = torch.zeros_like(xcl); goff = torch.zeros_like(off); gm = torch.zeros_like(m)
+    gw = torch.zeros_like(w); gb = torch.zeros(Co, device=xcl.device)
+    wsb = C.dcnv2_backward_workspace_bytes(B, Ci, Co, H, W, 3, 3, 1, 1, 1, 1)
+    wsbuf = workspace(wsb, xcl.device)
+    C.dcnv2_backward_ex(ptr(xcl), 1, ptr(off), ptr(m), ptr(w), ptr(go), ptr(gx), 1, ptr(goff), ptr(gm), ptr(gw), ptr(gb),
+                        B, Ci, H, W, Co, 3, 3, 1, 1, 1, 1, ptr(wsbuf), wsb, stream_ptr(xcl))
+    return gx, goff, gm, gw, gb
+
+
 def timeit(fn, n=10):
     for _ in range(3):
         fn()
@@ -73,9 +86,15 @@ def main():
         det = [bool((u == v).all().item()) for u, v in zip(a, a2)]
         t_tc = timeit(lambda: run(x, off, m, w, go, True))
         t_nodx = timeit(lambda: run(x, off, m, w, go, True, False))
+        t_cl = float("nan")
+        if not args.deterministic and Ci % 32 == 0:
+            xcl = x.contiguous(memory_format=torch.channels_last)
+            c = run_cl(xcl, off, m, w, go)
+            errs.append("cl-dx %.2e" % (c[0] - r[0]).abs().max().item())
+            t_cl = timeit(lambda: run_cl(xcl, off, m, w, go))
         t_fp = timeit(lambda: run(x, off, m, w, go, False), 3)
-        print("B%d %d@%dx%d->%d  tc %.3f ms (without dX %.3f)  fp32 %.3f ms | %s | bit-identical dx,doff,dmask,dw,db: %s"
-              % (B, Ci, H, W, Co, t_tc, t_nodx, t_fp, "  ".join(errs), det), flush=True)
+        print("B%d %d@%dx%d->%d  tc %.3f ms (without dX %.3f, channels-last %.3f)  fp32 %.3f ms | %s | bit-identical dx,doff,dmask,dw,db: %s"
+              % (B, Ci, H, W, Co, t_tc, t_nodx, t_cl, t_fp, "  ".join(errs), det), flush=True)
 
 
 if __name__ == "__main__":
