@@ -23,7 +23,7 @@ constexpr int EX_THREADS = 512;
 constexpr int EX_CAP = 4096;       // candidate keys per CTA
 constexpr int EX_STEP = 2048;      // tuples scored between two capacity checks
 constexpr int EX_MAX_DETS = 2048;  // num_dets limit (CAP - STEP)
-constexpr int EX_MAX_GROUPS = 8;
+constexpr int EX_MAX_GROUPS = 16;   // segments per image (the merge sorts groups * num_dets keys in shared memory: 128 KB at 16 x 1000)
 
 struct RawList {
   float *scores; int64_t *inds; int32_t *clses; float *ys; float *xs;
@@ -37,6 +37,7 @@ struct ExctArgs {
   const float *t_regr, *l_regr, *b_regr, *r_regr;
   int B, CC, H, W, K, num_dets, groups, agnostic;
   float scores_thresh, center_thresh;
+  const uint32_t *ct_max;   // [B] order-preserving bits of the largest centre-map value of the image (pruning bound)
   u64 *seg;                 // [B, groups, num_dets]
   int *seg_cnt;             // [B, groups]
   float *dets;              // [B, num_dets, 14]
@@ -80,6 +81,22 @@ __global__ void __launch_bounds__(256) k_ct_agnostic(const float *__restrict__ c
   cls[i] = arg;
 }
 
+// out[b] = max over the image's centre map, as order-preserving bits (out zero-filled: below every float)
+__global__ void __launch_bounds__(256) k_ct_max(const float *__restrict__ ct, long long per_image, uint32_t *__restrict__ out) {
+  __shared__ uint32_t red[8];
+  const float *p = ct + (long long)blockIdx.y * per_image;
+  uint32_t best = 0u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_image; i += (long long)gridDim.x * blockDim.x)
+    best = max(best, mono_bits(__ldg(p + i)));
+  for (int k = 16; k > 0; k >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, k));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) best = max(best, red[i]);
+    atomicMax(out + blockIdx.y, best);
+  }
+}
+
 __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a) {
   extern __shared__ __align__(16) unsigned char ex_smem[];
   u64 *buf = reinterpret_cast<u64 *>(ex_smem);                     // [EX_CAP]
@@ -104,58 +121,80 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a)
 
   const long long HW = (long long)a.H * a.W;
   const int i_begin = (int)((long long)K * grp / a.groups), i_end = (int)((long long)K * (grp + 1) / a.groups);
-  const long long K3 = (long long)K * K * K;
-  const long long total = (long long)(i_end - i_begin) * K3;
+  const int K2 = K * K;
+  const long long K3 = (long long)K2 * K;
   const int nd = a.num_dets;
+  // upper bounds for the pruning test: the best bottom / right scores and the largest centre value of the image
+  float bmax = S[2][0], rmax = S[3][0];
+  for (int q = 1; q < K; ++q) { bmax = fmaxf(bmax, S[2][q]); rmax = fmaxf(rmax, S[3][q]); }
+  const float ctmax = mono_inv(a.ct_max[b]);
   u64 thr = 0ull;
-  for (long long base = 0; base < total; base += EX_STEP) {
-    __syncthreads();
-    const int cnt = s_cnt;           // every push of the previous step is in
-    __syncthreads();                 // nobody pushes before everyone has read: the branch is uniform
-    if (cnt + EX_STEP > EX_CAP) {    // sort, keep the num_dets best, raise the threshold
-      const int n = np2(cnt);
-      for (int t = cnt + tid; t < n; t += blockDim.x) buf[t] = 0ull;
-      __syncthreads();
-      sort_desc(buf, n);
-      if (cnt >= nd) thr = buf[nd - 1];
-      __syncthreads();
-      if (tid == 0 && cnt > nd) s_cnt = nd;
-      __syncthreads();
-    }
-    for (long long e = base + tid; e < min(base + (long long)EX_STEP, total); e += blockDim.x) {
-      const int i = i_begin + (int)(e / K3);
-      int rem = (int)(e - (long long)(i - i_begin) * K3);
-      const int j = rem / (K * K);
-      rem -= j * K * K;
-      const int k = rem / K, m = rem - k * K;
-      const float ts = S[0][i], lsx = S[1][j], bs = S[2][k], rs = S[3][m];
-      const float ty = Y[0][i], tx = X[0][i], ly = Y[1][j], lx = X[1][j];
-      const float by = Y[2][k], bx = X[2][k], ry = Y[3][m], rx = X[3][m];
-      const int cx = ((int)lx + (int)rx) >> 1;   // ((l_x + r_x + 0.5) / 2).long(), decode.py:322
-      const int cy = ((int)ty + (int)by) >> 1;   // :323
-      float ct;
-      if (a.agnostic) ct = __ldg(a.ct_agn + (long long)b * HW + cy * a.W + cx);
-      else ct = __ldg(a.ct_heat + ((long long)b * a.CC + CL[0][i]) * HW + cy * a.W + cx);
-      float sc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ts, lsx), bs), rs), __fmul_rn(2.0f, ct));
-      sc = __fdiv_rn(sc, 6.0f);                                                            // :333
-      const bool sc_bad = (ts < a.scores_thresh) || (lsx < a.scores_thresh) || (bs < a.scores_thresh) ||
-                          (rs < a.scores_thresh) || (ct < a.center_thresh);                // :350-355
-      const bool top_bad = (ty > ly) || (ty > by) || (ty > ry);                            // :341-348
-      const bool left_bad = (lx > tx) || (lx > bx) || (lx > rx);
-      const bool bot_bad = (by < ty) || (by < ly) || (by < ry);
-      const bool right_bad = (rx < tx) || (rx < lx) || (rx < bx);
-      sc = __fsub_rn(sc, sc_bad ? 1.0f : 0.0f);                                            // :355-360 order
-      if (!a.agnostic) {
-        const bool cls_bad = (CL[0][i] != CL[1][j]) || (CL[0][i] != CL[2][k]) || (CL[0][i] != CL[3][m]);
-        sc = __fsub_rn(sc, cls_bad ? 1.0f : 0.0f);
+  for (int i = i_begin; i < i_end; ++i) {
+    const float ts = S[0][i], ty = Y[0][i], tx = X[0][i];
+    const int ci = CL[0][i];
+    for (int j = 0; j < K; ++j) {
+      const float lsx = S[1][j], ly = Y[1][j], lx = X[1][j];
+      // Exact pruning of the whole (i, j, *, *) block: every penalty already decided by (i, j) costs 1.0, the score
+      // before penalties is at most the same expression over the best bottom / right / centre values, and every step
+      // of the computation is monotone in fp32 -- so if even that bound cannot beat the current num_dets-th key the
+      // K^2 tuples need not be scored (CTA-uniform: no barrier is skipped by only some threads).
+      {
+        int lb = 0;
+        lb += ((ts < a.scores_thresh) || (lsx < a.scores_thresh)) ? 1 : 0;
+        lb += (!a.agnostic && ci != CL[1][j]) ? 1 : 0;
+        lb += (ty > ly) ? 1 : 0;
+        lb += (lx > tx) ? 1 : 0;
+        float ub = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ts, lsx), bmax), rmax), __fmul_rn(2.0f, ctmax));
+        ub = __fdiv_rn(ub, 6.0f);
+        for (int q = 0; q < lb; ++q) ub = __fsub_rn(ub, 1.0f);
+        ub = __fadd_rn(ub, 0.0f);      // -0 -> +0: the key order puts -0 below +0
+        if (mono_bits(ub) < (uint32_t)(thr >> 32)) continue;
       }
-      sc = __fsub_rn(sc, top_bad ? 1.0f : 0.0f);
-      sc = __fsub_rn(sc, left_bad ? 1.0f : 0.0f);
-      sc = __fsub_rn(sc, bot_bad ? 1.0f : 0.0f);
-      sc = __fsub_rn(sc, right_bad ? 1.0f : 0.0f);
-      const uint32_t tuple = (uint32_t)((long long)i * K3 + (e - (long long)(i - i_begin) * K3));
-      const u64 key = ((u64)mono_bits(sc) << 32) | (u64)(0xffffffffu - tuple);
-      if (key > thr) buf[atomicAdd(&s_cnt, 1)] = key;
+      for (int base = 0; base < K2; base += EX_STEP) {
+        __syncthreads();
+        const int cnt = s_cnt;           // every push of the previous step is in
+        __syncthreads();                 // nobody pushes before everyone has read: the branch is uniform
+        if (cnt + EX_STEP > EX_CAP) {    // sort, keep the num_dets best, raise the threshold
+          const int n = np2(cnt);
+          for (int t = cnt + tid; t < n; t += blockDim.x) buf[t] = 0ull;
+          __syncthreads();
+          sort_desc(buf, n);
+          if (cnt >= nd) thr = buf[nd - 1];
+          __syncthreads();
+          if (tid == 0 && cnt > nd) s_cnt = nd;
+          __syncthreads();
+        }
+        for (int e = base + tid; e < min(base + EX_STEP, K2); e += blockDim.x) {
+          const int k = e / K, m = e - k * K;
+          const float bs = S[2][k], rs = S[3][m];
+          const float by = Y[2][k], bx = X[2][k], ry = Y[3][m], rx = X[3][m];
+          const int cx = ((int)lx + (int)rx) >> 1;   // ((l_x + r_x + 0.5) / 2).long(), decode.py:322
+          const int cy = ((int)ty + (int)by) >> 1;   // :323
+          float ct;
+          if (a.agnostic) ct = __ldg(a.ct_agn + (long long)b * HW + cy * a.W + cx);
+          else ct = __ldg(a.ct_heat + ((long long)b * a.CC + ci) * HW + cy * a.W + cx);
+          float sc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ts, lsx), bs), rs), __fmul_rn(2.0f, ct));
+          sc = __fdiv_rn(sc, 6.0f);                                                            // :333
+          const bool sc_bad = (ts < a.scores_thresh) || (lsx < a.scores_thresh) || (bs < a.scores_thresh) ||
+                              (rs < a.scores_thresh) || (ct < a.center_thresh);                // :350-355
+          const bool top_bad = (ty > ly) || (ty > by) || (ty > ry);                            // :341-348
+          const bool left_bad = (lx > tx) || (lx > bx) || (lx > rx);
+          const bool bot_bad = (by < ty) || (by < ly) || (by < ry);
+          const bool right_bad = (rx < tx) || (rx < lx) || (rx < bx);
+          sc = __fsub_rn(sc, sc_bad ? 1.0f : 0.0f);                                            // :355-360 order
+          if (!a.agnostic) {
+            const bool cls_bad = (ci != CL[1][j]) || (ci != CL[2][k]) || (ci != CL[3][m]);
+            sc = __fsub_rn(sc, cls_bad ? 1.0f : 0.0f);
+          }
+          sc = __fsub_rn(sc, top_bad ? 1.0f : 0.0f);
+          sc = __fsub_rn(sc, left_bad ? 1.0f : 0.0f);
+          sc = __fsub_rn(sc, bot_bad ? 1.0f : 0.0f);
+          sc = __fsub_rn(sc, right_bad ? 1.0f : 0.0f);
+          const uint32_t tuple = (uint32_t)((long long)i * K3 + (long long)j * K2 + e);
+          const u64 key = ((u64)mono_bits(sc) << 32) | (u64)(0xffffffffu - tuple);
+          if (key > thr) buf[atomicAdd(&s_cnt, 1)] = key;
+        }
+      }
     }
   }
   // final cut of this group's segment
@@ -249,7 +288,7 @@ size_t cnb_exct_workspace_bytes(int b, int c, int cc, int h, int w, int k, int n
   const size_t agn = 2 * align_up((size_t)b * h * w * 4, 256);            // class-agnostic centre map
   (void)cc;
   return select_workspace_bytes(pl) + 4 * raw_sz((long long)b * k) + maps + agn +
-         align_up((size_t)b * g * num_dets * 8, 256) + align_up((size_t)b * g * 4, 256);
+         align_up((size_t)b * g * num_dets * 8, 256) + align_up((size_t)b * g * 4, 256) + align_up((size_t)b * 4, 256);
 }
 
 int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_heat, const float *r_heat,
@@ -287,7 +326,9 @@ int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_hea
   int32_t *agn_cls = reinterpret_cast<int32_t *>(p); p += align_up((size_t)b * h * w * 4, 256);
   const int groups = exct_groups(b, k);
   a.seg = reinterpret_cast<u64 *>(p); p += align_up((size_t)b * groups * num_dets * 8, 256);
-  a.seg_cnt = reinterpret_cast<int *>(p);
+  a.seg_cnt = reinterpret_cast<int *>(p); p += align_up((size_t)b * groups * 4, 256);
+  uint32_t *ct_max = reinterpret_cast<uint32_t *>(p);
+  a.ct_max = ct_max;
 
   const float *maps[4] = {t_heat, l_heat, b_heat, r_heat};
   if (aggr_weight > 0.0f) {   // :287-291: t,b horizontal; l,r vertical
@@ -315,6 +356,16 @@ int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_hea
     CNB_CHECK_LAUNCH("cnb_exct_decode agnostic centre");
     count_launch();
     a.ct_agn = agn; a.ct_cls = agn_cls;
+  }
+  {   // largest centre value per image: the pruning bound of k_exct_tuples
+    CNB_CUDA(cudaMemsetAsync(ct_max, 0, (size_t)b * 4, stream));
+    const long long per = agnostic ? (long long)h * w : (long long)cc * h * w;
+    int blocks = (int)((per + 256 * 8 - 1) / (256 * 8));
+    if (blocks > 64) blocks = 64;
+    if (blocks < 1) blocks = 1;
+    k_ct_max<<<dim3((unsigned)blocks, (unsigned)b), 256, 0, stream>>>(agnostic ? agn : ct_heat, per, ct_max);
+    CNB_CHECK_LAUNCH("cnb_exct_decode centre maximum");
+    count_launch();
   }
   a.t_regr = t_regr; a.l_regr = l_regr; a.b_regr = b_regr; a.r_regr = r_regr;
   a.B = b; a.CC = cc; a.H = h; a.W = w; a.K = k; a.num_dets = num_dets; a.groups = groups; a.agnostic = agnostic;
