@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a)
   __syncthreads();
 
   const long long HW = (long long)a.H * a.W;
-  const int i_begin = (int)((long long)K * grp / a.groups), i_end = (int)((long long)K * (grp + 1) / a.groups);
   const int K2 = K * K;
   const long long K3 = (long long)K2 * K;
   const int nd = a.num_dets;
@@ -129,7 +128,9 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a)
   for (int q = 1; q < K; ++q) { bmax = fmaxf(bmax, S[2][q]); rmax = fmaxf(rmax, S[3][q]); }
   const float ctmax = mono_inv(a.ct_max[b]);
   u64 thr = 0ull;
-  for (int i = i_begin; i < i_end; ++i) {
+  // the groups of an image take the top candidates round-robin: every group sees the same mix of strong and weak ones,
+  // so their thresholds rise alike and they finish together (the merge orders the keys, not the groups)
+  for (int i = grp; i < K; i += a.groups) {
     const float ts = S[0][i], ty = Y[0][i], tx = X[0][i];
     const int ci = CL[0][i];
     for (int j = 0; j < K; ++j) {
