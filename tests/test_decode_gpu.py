@@ -281,6 +281,32 @@ def test_exct_vs_oracle(B, C, H, W, K, ND, aggr):
     np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
 
 
+@pytest.mark.parametrize("scale_ct,thr_s,thr_c,neg", [(3.0, 0.1, 0.1, False), (1.0, 0.35, 0.5, False), (0.5, 0.1, 0.1, True)])
+def test_exct_block_pruning_is_exact(scale_ct, thr_s, thr_c, neg):
+    """k_exct_tuples skips whole (top, left) blocks against a bound built from the best bottom / right scores and the
+    largest centre value.  Inputs that stress the bound: centre values above 1 (nothing clamps the centre map), high
+    thresholds (most tuples carry the score penalty), extreme maps with negative values (non-positive candidates),
+    num_dets small enough that the running threshold climbs early -- every row must still equal the oracle's."""
+    from centernet_b200 import decode as D
+    B, C, H, W, K, ND = 2, 5, 40, 48, 16, 150
+    maps = _extreme_maps(B, C, H, W, 77, n_obj=10)
+    maps[4] = (maps[4] * scale_ct).astype(np.float32)
+    if neg:
+        maps = [m - np.float32(0.02) for m in maps]
+    regs = [rnd((B, 2, H, W), 60 + i) for i in range(4)]
+    kw = dict(K=K, num_dets=ND, scores_thresh=thr_s, center_thresh=thr_c)
+    want = O.exct_decode(*maps, *regs, **kw)
+    got = D.exct_decode(*dev(*maps), *dev(*regs), **kw).cpu().numpy()
+    np.testing.assert_array_equal(got[..., 4], want[..., 4])
+    np.testing.assert_array_equal(got[..., 13], want[..., 13])
+    np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
+    t1, l1, b1, r1 = [m.max(axis=1, keepdims=True) for m in maps[:4]]
+    want = O.agnex_ct_decode(t1, l1, b1, r1, maps[4], *regs, **kw)
+    got = D.agnex_ct_decode(*dev(t1, l1, b1, r1, maps[4]), *dev(*regs), **kw).cpu().numpy()
+    np.testing.assert_array_equal(got[..., 4], want[..., 4])
+    np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
+
+
 def test_topk_nonpositive_scores():
     from centernet_b200 import decode as D
     scores = -noise(2, 3, 12, 16, 31)                       # every score negative, no peak test
