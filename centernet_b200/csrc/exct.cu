@@ -38,6 +38,7 @@ struct ExctArgs {
   int B, CC, H, W, K, num_dets, groups, agnostic;
   float scores_thresh, center_thresh;
   const uint32_t *ct_max;   // [B] order-preserving bits of the largest centre-map value of the image (pruning bound)
+  u64 *gthr;                // [B] best num_dets-th key any group of the image has reached (shared pruning threshold)
   u64 *seg;                 // [B, groups, num_dets]
   int *seg_cnt;             // [B, groups]
   float *dets;              // [B, num_dets, 14]
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a)
   u64 *buf = reinterpret_cast<u64 *>(ex_smem);                     // [EX_CAP]
   float *ls = reinterpret_cast<float *>(buf + EX_CAP);             // 4 lists x (score, y, x, cls) x K
   __shared__ int s_cnt;
+  __shared__ u64 s_g;
   const int K = a.K, b = blockIdx.x / a.groups, grp = blockIdx.x - b * a.groups;
   const int tid = threadIdx.x;
   float *S[4], *Y[4], *X[4];
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a)
   for (int q = 1; q < K; ++q) { bmax = fmaxf(bmax, S[2][q]); rmax = fmaxf(rmax, S[3][q]); }
   const float ctmax = mono_inv(a.ct_max[b]);
   u64 thr = 0ull;
-  // the groups of an image take the top candidates round-robin: every group sees the same mix of strong and weak ones,
-  // so their thresholds rise alike and they finish together (the merge orders the keys, not the groups)
+  // the groups of an image take the top candidates round-robin (every group gets the same mix of strong and weak ones)
+  // and share their thresholds through gthr, so they finish together; the merge orders the keys, not the groups
   for (int i = grp; i < K; i += a.groups) {
     const float ts = S[0][i], ty = Y[0][i], tx = X[0][i];
     const int ci = CL[0][i];
@@ -152,17 +154,24 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_exct_tuples(const ExctArgs a)
         if (mono_bits(ub) < (uint32_t)(thr >> 32)) continue;
       }
       for (int base = 0; base < K2; base += EX_STEP) {
+        // the num_dets-th key of ANY group of the image bounds the result from below: adopt the best one published
+        if (tid == 0) s_g = *reinterpret_cast<volatile u64 *>(a.gthr + b);
         __syncthreads();
         const int cnt = s_cnt;           // every push of the previous step is in
-        __syncthreads();                 // nobody pushes before everyone has read: the branch is uniform
+        const u64 gth = s_g;
+        __syncthreads();                 // nobody pushes before everyone has read: the branches are uniform
+        if (gth > thr) thr = gth;
         if (cnt + EX_STEP > EX_CAP) {    // sort, keep the num_dets best, raise the threshold
           const int n = np2(cnt);
           for (int t = cnt + tid; t < n; t += blockDim.x) buf[t] = 0ull;
           __syncthreads();
           sort_desc(buf, n);
-          if (cnt >= nd) thr = buf[nd - 1];
+          if (cnt >= nd && buf[nd - 1] > thr) thr = buf[nd - 1];
           __syncthreads();
-          if (tid == 0 && cnt > nd) s_cnt = nd;
+          if (tid == 0) {
+            if (cnt > nd) s_cnt = nd;
+            if (cnt >= nd) atomicMax(a.gthr + b, thr);
+          }
           __syncthreads();
         }
         for (int e = base + tid; e < min(base + EX_STEP, K2); e += blockDim.x) {
@@ -289,7 +298,8 @@ size_t cnb_exct_workspace_bytes(int b, int c, int cc, int h, int w, int k, int n
   const size_t agn = 2 * align_up((size_t)b * h * w * 4, 256);            // class-agnostic centre map
   (void)cc;
   return select_workspace_bytes(pl) + 4 * raw_sz((long long)b * k) + maps + agn +
-         align_up((size_t)b * g * num_dets * 8, 256) + align_up((size_t)b * g * 4, 256) + align_up((size_t)b * 4, 256);
+         align_up((size_t)b * g * num_dets * 8, 256) + align_up((size_t)b * g * 4, 256) + align_up((size_t)b * 4, 256) +
+         align_up((size_t)b * 8, 256);
 }
 
 int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_heat, const float *r_heat,
@@ -328,8 +338,10 @@ int cnb_exct_decode(const float *t_heat, const float *l_heat, const float *b_hea
   const int groups = exct_groups(b, k);
   a.seg = reinterpret_cast<u64 *>(p); p += align_up((size_t)b * groups * num_dets * 8, 256);
   a.seg_cnt = reinterpret_cast<int *>(p); p += align_up((size_t)b * groups * 4, 256);
-  uint32_t *ct_max = reinterpret_cast<uint32_t *>(p);
+  uint32_t *ct_max = reinterpret_cast<uint32_t *>(p); p += align_up((size_t)b * 4, 256);
   a.ct_max = ct_max;
+  a.gthr = reinterpret_cast<u64 *>(p);
+  CNB_CUDA(cudaMemsetAsync(a.gthr, 0, (size_t)b * 8, stream));
 
   const float *maps[4] = {t_heat, l_heat, b_heat, r_heat};
   if (aggr_weight > 0.0f) {   // :287-291: t,b horizontal; l,r vertical
