@@ -12,6 +12,7 @@
 // dense target map of the reference (built on the CPU, copied H2D, read by ~12 ATen kernels)
 // is never materialised.  num_pos -- needed to normalise the gradient in the same pass -- is
 // known up front from the object lists (one positive per distinct valid centre).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cnb {
@@ -97,14 +98,14 @@ __device__ __forceinline__ float target_at(const Obj *objs, const ObjTab *tabs, 
 // Collect the valid objects of image b that belong to class c (block-wide, order-free: max is commutative).
 __device__ __forceinline__ int gather_objects(const int32_t *cls, const int32_t *cx, const int32_t *cy,
                                               const int32_t *rad, const uint8_t *valid, int b, int M, int c, int H,
-                                              int W, Obj *s_obj, int *s_n) {
+                                              int W, Obj *s_obj, int *s_n, int y0 = 0, int y1 = 0x7fffffff) {
   if (threadIdx.x == 0) *s_n = 0;
   __syncthreads();
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     const size_t o = (size_t)b * M + m;
     if (valid[o] && cls[o] == c) {
       const int x = cx[o], y = cy[o];
-      if (x >= 0 && x < W && y >= 0 && y < H && rad[o] >= 0) {
+      if (x >= 0 && x < W && y >= 0 && y < H && rad[o] >= 0 && y + rad[o] >= y0 && y - rad[o] < y1) {   // rows [y0, y1) of this CTA
         const int slot = atomicAdd(s_n, 1);
         if (slot < MAX_OBJ_PER_PLANE) s_obj[slot] = Obj{x, y, rad[o]};
       }
@@ -254,15 +255,18 @@ __global__ void __launch_bounds__(FOCAL_THREADS) k_focal_splat(const float *__re
                                                                const int32_t *rad, const uint8_t *valid, int M, int C,
                                                                int H, int W, float grad_scale,
                                                                float *__restrict__ grad, float *__restrict__ hm,
-                                                               FocalAcc *acc, float *out2) {
+                                                               FocalAcc *acc, float *out2, int parts) {
+  // one CTA per (image, class plane, band of H / parts rows): more, shorter CTAs fill the last wave better
   __shared__ Obj s_obj[MAX_OBJ_PER_PLANE];
   __shared__ ObjTab s_tab[MAX_OBJ_PER_PLANE];
   __shared__ float s_gauss[GAUSS_TAB_FLOATS];
   __shared__ int s_n, s_total;
-  const int b = blockIdx.x / C, c = blockIdx.x - b * C;
-  const int nobj = gather_objects(cls, cx, cy, rad, valid, b, M, c, H, W, s_obj, &s_n);
+  const int plane = blockIdx.x / parts, part = blockIdx.x - plane * parts;
+  const int b = plane / C, c = plane - b * C;
+  const int y_lo = (int)((long long)H * part / parts), y_hi = (int)((long long)H * (part + 1) / parts);
+  const int nobj = gather_objects(cls, cx, cy, rad, valid, b, M, c, H, W, s_obj, &s_n, y_lo, y_hi);
   if (nobj) build_tables(s_obj, nobj, s_tab, s_gauss, &s_total);
-  const long long base = (long long)blockIdx.x * H * W;
+  const long long base = (long long)plane * H * W;
   float inv_norm = 0.0f;
   if (!WRITE_HM) {
     const double np_ = acc->num_pos;
@@ -272,8 +276,12 @@ __global__ void __launch_bounds__(FOCAL_THREADS) k_focal_splat(const float *__re
   const int HW = H * W;
   const bool vec = (W % 4 == 0) && ((((uintptr_t)pred | (uintptr_t)grad | (uintptr_t)hm) & 15u) == 0);
   if (vec) {
-    for (int i = threadIdx.x; i < HW / 4; i += blockDim.x) {
-      const int y = (i * 4) / W, x = (i * 4) - y * W;
+    // (x, y) of the thread's float4 advance incrementally: no division in the loop (the kernel is issue-bound)
+    const int w4 = W / 4;
+    int y = y_lo + (int)threadIdx.x / w4, x = ((int)threadIdx.x - ((int)threadIdx.x / w4) * w4) * 4;
+    const int dyq = (int)blockDim.x / w4, dxq = ((int)blockDim.x - dyq * w4) * 4;
+    for (int i = y_lo * w4 + threadIdx.x; i < y_hi * w4; i += blockDim.x, y += dyq, x += dxq) {
+      if (x >= W) { x -= W; ++y; }
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (nobj) g = target_at4(s_obj, s_tab, s_gauss, nobj, x, y);
       if (WRITE_HM) {
@@ -288,7 +296,7 @@ __global__ void __launch_bounds__(FOCAL_THREADS) k_focal_splat(const float *__re
       }
     }
   } else {
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    for (int i = y_lo * W + threadIdx.x; i < y_hi * W; i += blockDim.x) {
       const int y = i / W, x = i - y * W;
       const float g = nobj ? target_at(s_obj, s_tab, s_gauss, nobj, x, y) : 0.0f;
       if (WRITE_HM) {
@@ -374,6 +382,14 @@ static int focal_grid(long long n4) {
 
 using namespace cnb;
 
+// bands per plane of the splat kernels (CNB_FOCAL_PARTS overrides, for tuning)
+static int focal_parts(int h) {
+  static const int env = [] { const char *e = getenv("CNB_FOCAL_PARTS"); return e ? atoi(e) : 0; }();
+  int p = env > 0 ? env : 1;
+  if (p > h) p = h;
+  return p < 1 ? 1 : p;
+}
+
 extern "C" {
 
 size_t cnb_focal_workspace_bytes(long long) { return 256; }
@@ -406,8 +422,9 @@ int cnb_splat_gaussian(const int32_t *obj_cls, const int32_t *obj_cx, const int3
   CNB_REQUIRE(b > 0 && m > 0 && c > 0 && h > 0 && w > 0, CNB_EINVAL, "cnb_splat_gaussian: non-positive dimension");
   CNB_REQUIRE(m <= MAX_OBJ_PER_PLANE, CNB_EUNSUPPORTED, "cnb_splat_gaussian: at most %d objects per image (got %d)",
               MAX_OBJ_PER_PLANE, m);
-  k_focal_splat<false, true><<<b * c, FOCAL_THREADS, 0, (cudaStream_t)stream_>>>(
-      nullptr, obj_cls, obj_cx, obj_cy, obj_radius, obj_valid, m, c, h, w, 0.0f, nullptr, hm, nullptr, nullptr);
+  const int parts = focal_parts(h);
+  k_focal_splat<false, true><<<b * c * parts, FOCAL_THREADS, 0, (cudaStream_t)stream_>>>(
+      nullptr, obj_cls, obj_cx, obj_cy, obj_radius, obj_valid, m, c, h, w, 0.0f, nullptr, hm, nullptr, nullptr, parts);
   CNB_CHECK_LAUNCH("cnb_splat_gaussian");
   count_launch();
   return CNB_OK;
@@ -430,14 +447,15 @@ int cnb_focal_splat_loss(const float *pred, const int32_t *obj_cls, const int32_
   k_count_pos_objects<<<b, 128, (size_t)m * sizeof(int), stream>>>(obj_cls, obj_cx, obj_cy, obj_radius, obj_valid, m, c, h,
                                                                     w, acc);
   CNB_CHECK_LAUNCH("cnb_focal_splat_loss count");
+  const int parts = focal_parts(h);
   if (logits)
-    k_focal_splat<true, false><<<b * c, FOCAL_THREADS, 0, stream>>>(pred, obj_cls, obj_cx, obj_cy, obj_radius,
-                                                                     obj_valid, m, c, h, w, grad_scale, grad, nullptr,
-                                                                     acc, out2);
+    k_focal_splat<true, false><<<b * c * parts, FOCAL_THREADS, 0, stream>>>(pred, obj_cls, obj_cx, obj_cy, obj_radius,
+                                                                             obj_valid, m, c, h, w, grad_scale, grad,
+                                                                             nullptr, acc, out2, parts);
   else
-    k_focal_splat<false, false><<<b * c, FOCAL_THREADS, 0, stream>>>(pred, obj_cls, obj_cx, obj_cy, obj_radius,
-                                                                      obj_valid, m, c, h, w, grad_scale, grad,
-                                                                      nullptr, acc, out2);
+    k_focal_splat<false, false><<<b * c * parts, FOCAL_THREADS, 0, stream>>>(pred, obj_cls, obj_cx, obj_cy, obj_radius,
+                                                                              obj_valid, m, c, h, w, grad_scale, grad,
+                                                                              nullptr, acc, out2, parts);
   CNB_CHECK_LAUNCH("cnb_focal_splat_loss");
   count_launch(2);
   return CNB_OK;
