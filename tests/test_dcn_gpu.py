@@ -79,20 +79,20 @@ def test_backward_vs_oracle_autograd(B, Ci, H, W, Co, dg, stride):
         assert err <= 1e-3 * scale, (name, err, scale)      # fp32 gradcheck tolerance of test.py:115 (atol 1e-3)
 
 
-def _raw_backward(x, off, m, w, go, stride, dg, tensor_cores):
+def _raw_backward(x, off, m, w, go, stride, dg, tensor_cores, pad=1, dil=1):
     from centernet_b200._lib import C, ptr, stream_ptr, workspace
     B, Ci, H, W = x.shape
-    Co = w.shape[0]
+    Co, _, kh, kw = w.shape
     grads = [torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(m), torch.zeros_like(w),
              torch.zeros(Co, device=x.device)]
     ws, wsb, keep = 0, 0, None
     if tensor_cores:
-        wsb = C.dcnv2_backward_workspace_bytes(B, Ci, Co, H, W, 3, 3, stride, 1, 1, dg)
+        wsb = C.dcnv2_backward_workspace_bytes(B, Ci, Co, H, W, kh, kw, stride, pad, dil, dg)
         assert wsb > 0
         keep = workspace(wsb, x.device)
         ws = ptr(keep)
-    C.dcnv2_backward(ptr(x), ptr(off), ptr(m), ptr(w), ptr(go), *[ptr(g) for g in grads], B, Ci, H, W, Co, 3, 3,
-                     stride, stride, 1, 1, 1, 1, dg, ws, wsb, stream_ptr(x))
+    C.dcnv2_backward(ptr(x), ptr(off), ptr(m), ptr(w), ptr(go), *[ptr(g) for g in grads], B, Ci, H, W, Co, kh, kw,
+                     stride, stride, pad, pad, dil, dil, dg, ws, wsb, stream_ptr(x))
     torch.cuda.synchronize()
     return grads
 
@@ -145,6 +145,47 @@ def test_backward_deterministic_mode(B, Ci, H, W, Co, dg):
         assert (u - v).abs().max().item() <= 2e-4 * scale, ("clamped", name, (u - v).abs().max().item(), scale)
     for name, u, v in zip(("input", "offset", "mask", "weight", "bias"), d1, d2):
         assert torch.equal(u, v), name + " not bit-identical run to run in deterministic mode"
+
+
+@pytest.mark.parametrize("kh,kw,pad,dil,stride", [(1, 3, 1, 1, 1), (3, 3, 2, 2, 1), (1, 1, 0, 1, 1), (3, 2, 1, 1, 2)])
+def test_backward_tensor_core_other_kernels(kh, kw, pad, dil, stride):
+    """Fewer than 9 taps (zero weight tiles for the missing ones), dilation 2, 1x1: tensor-core backward vs the fp32 path."""
+    B, Ci, H, W, Co, dg = 2, 64, 20, 26, 48, 1
+    gen = torch.Generator().manual_seed(31)
+    Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1
+    kt = kh * kw
+    x = torch.randn(B, Ci, H, W, generator=gen).cuda()
+    off = (torch.randn(B, 2 * kt * dg, Ho, Wo, generator=gen) * 1.5).cuda()
+    m = torch.sigmoid(torch.randn(B, kt * dg, Ho, Wo, generator=gen)).cuda()
+    w = (torch.randn(Co, Ci, kh, kw, generator=gen) / (Ci * kt) ** 0.5).cuda()
+    go = torch.randn(B, Co, Ho, Wo, generator=gen).cuda()
+    a = _raw_backward(x, off, m, w, go, stride, dg, True, pad, dil)
+    r = _raw_backward(x, off, m, w, go, stride, dg, False, pad, dil)
+    for name, u, v in zip(("input", "offset", "mask", "weight", "bias"), a, r):
+        scale = max(1.0, v.abs().max().item())
+        assert (u - v).abs().max().item() <= 2e-4 * scale, (name, (u - v).abs().max().item(), scale)
+
+
+def test_backward_batch_chunks():
+    """The column gradient is held to ~1.5 GiB: 33 images of 64@128x128 (42 MB of dcol each) run as two passes of 30 + 3
+    images.  The chunked tensor-core backward must equal the fp32 path image by image (first, boundary and last ones)."""
+    B, Ci, H, W, Co = 33, 64, 128, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(B, Ci, H, W, device="cuda", generator=g)
+    off = torch.randn(B, 18, H, W, device="cuda", generator=g) * 1.5
+    m = torch.sigmoid(torch.randn(B, 9, H, W, device="cuda", generator=g))
+    w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (3.0 * Ci ** 0.5)
+    go = torch.randn(B, Co, H, W, device="cuda", generator=g)
+    a = _raw_backward(x, off, m, w, go, 1, 1, True)
+    r = _raw_backward(x, off, m, w, go, 1, 1, False)
+    for name, u, v in zip(("input", "offset", "mask"), a[:3], r[:3]):
+        for img in (0, 29, 30, 32):
+            scale = max(1.0, v[img].abs().max().item())
+            assert (u[img] - v[img]).abs().max().item() <= 2e-4 * scale, (name, img)
+    for name, u, v in zip(("weight", "bias"), a[3:], r[3:]):
+        scale = max(1.0, v.abs().max().item())
+        assert (u - v).abs().max().item() <= 5e-4 * scale, (name, (u - v).abs().max().item(), scale)
 
 
 @pytest.mark.parametrize("B,Ci,H,W,Co", [(2, 64, 24, 40, 64), (2, 128, 17, 19, 96)])
