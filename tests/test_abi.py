@@ -77,3 +77,27 @@ def test_validation_of_later_entry_points():
         _C.psroi_pooling_forward(16, 16, 0, 16, 16, 1, 8, 9, 9, 2, 3, 0, 0.25, 2, 2, 3, 3, 2, 0.0, 0)
     with pytest.raises(RuntimeError, match="in-place"):
         _C.edge_aggregate(16, 16, 1, 1, 8, 8, 0.1, 1, 0)
+
+
+def test_dcnv2_backward_workspace_query_and_switches():
+    """cnb_dcnv2_backward_workspace_bytes: positive for what the tensor-core backward covers, 0 where the fp32 kernels must
+    run (more than 9 taps, bad shapes, images beyond the 32-bit in-image indexing); the deterministic switch is a
+    process-wide flag; cnb_dcnv2_backward_ex validates before any CUDA call."""
+    from centernet_b200 import _C
+    q = _C.dcnv2_backward_workspace_bytes
+    base = q(16, 64, 64, 128, 128, 3, 3, 1, 1, 1, 1)
+    assert base > 0 and base % 16 == 0
+    assert q(32, 64, 64, 128, 128, 3, 3, 1, 1, 1, 1) > base            # grows with the batch ...
+    # ... but the column gradient (671 MB per 16 images here) is held to ~1.5 GiB: at B=256 the workspace is the two
+    # channels-last copies (2 x 1.07 GB) + max(gy tiles + dcol chunk, the weight pass's 2.1 GB of dY tiles), not 10.7 GB of dcol
+    assert q(256, 64, 64, 128, 128, 3, 3, 1, 1, 1, 1) < 6 * (1 << 30)
+    assert q(2, 64, 64, 32, 32, 5, 5, 1, 2, 1, 1) == 0                  # 25 taps
+    assert q(2, 64, 64, 32, 32, 3, 3, 1, 1, 1, 3) == 0                  # cin not divisible by the groups
+    assert q(1, 32, 32, 8192, 8192, 3, 3, 1, 1, 1, 1) == 0              # image too large for 32-bit in-image offsets
+    assert q(2, 12, 5, 9, 11, 3, 3, 2, 1, 1, 2) > 0                     # ragged, strided, grouped: covered
+    assert _C.dcnv2_get_deterministic() == 0
+    _C.dcnv2_set_deterministic(1)
+    assert _C.dcnv2_get_deterministic() == 1
+    _C.dcnv2_set_deterministic(0)
+    with pytest.raises(RuntimeError, match="null pointer"):
+        _C.dcnv2_backward_ex(0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 2, 64, 8, 8, 64, 3, 3, 1, 1, 1, 1, 0, 0, 0)
